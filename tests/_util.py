@@ -61,3 +61,27 @@ class ChainTapeDraws(object):
         v = float(self.u_tape[self.m, self.nu])
         self.nu += 1
         return v
+
+
+def sampler_from_fixture(fx, dtype="float64", kernel="generic", with_draws=True, **over):
+    """Build the CUDA-backed HMC_sampler (understanding-hmc_b200/samplers.py) for a golden fixture."""
+    import samplers as S
+    D = int(fx["D"])
+    spec = S.MVNSpec.from_cov(fx["q0"], fx["cov0"])
+    sampler = str(fx["sampler"])
+    dt = fx["dt"] if fx["dt"].ndim else float(fx["dt"])
+    cov_p = fx["cov_p"]
+    cov_p = None if np.array_equal(cov_p, np.eye(D)) else cov_p
+    kw = dict(Nchain=int(fx["Nchain"]), Niter=int(fx["Niter"]), thin_rate=int(fx["thin_rate"]),
+              warm_up_num=int(fx["warm_up_num"]), cov_p=cov_p, sampler_type=sampler, dt=dt,
+              dtype=dtype, kernel=kernel, target=spec)
+    if sampler == "Random":
+        kw.update(L_low=int(fx["L_low"]), L_high=int(fx["L_high"]))
+        if with_draws:
+            kw["draws"] = dict(p_tape=fx["p_tape"], L_tape=fx["L_tape"], u_tape=fx["u_tape"])
+    else:
+        kw.update(d_max=int(fx["d_max"]))
+        if with_draws:
+            kw["draws"] = dict(p_tape=fx["p_tape"], dir_tape=fx["dir_tape"], u_tape=fx["u_tape"])
+    kw.update(over)
+    return S.HMC_sampler(D, None, None, **kw)

@@ -1,0 +1,208 @@
+"""Parity of the CUDA random-trajectory sampler (through the C-ABI) with the reference / oracle.
+
+Tolerances (BASELINE.json north_star: "leapfrog trajectories rel 1e-5 over the case-script L; identical
+accept/reject decisions on the reference's draws"):
+  * float64 kernel, reference draws injected, free running: whole sample stream within 1e-9 (relative to the
+    largest |q|), energies within 1e-9 relative, identical acceptance counts and chain-0 decisions;
+  * float32 kernels, teacher forced (every iteration restarted from the oracle's q_initial): trajectory end
+    points within rel-L2 1e-5 for L < 20 (SURVEY H4 measured 2e-7..6e-6), decisions identical except
+    near ties |ln u + dE| < 1e-3 * max(1, |E|) which are counted and bounded.
+"""
+import numpy as np
+import pytest
+
+from oracle import hmc_oracle as O
+from _util import RANDOM_FIXTURES, load, flat_tape, sampler_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", RANDOM_FIXTURES)
+def test_f64_free_running_matches_reference(name):
+    fx = load(name)
+    nsave = int(fx["N_save_chain0"])
+    H = sampler_from_fixture(fx, dtype="float64", kernel="generic")
+    H.gen_sample(fx["q_start"], N_save_chain0=nsave, verbose=False)
+    qs = max(1.0, np.abs(fx["q_chain"]).max())
+    es = max(1.0, np.abs(fx["E_chain"]).max())
+    np.testing.assert_allclose(H.q_chain, fx["q_chain"], rtol=0, atol=1e-9 * qs)
+    np.testing.assert_allclose(H.E_chain, fx["E_chain"], rtol=0, atol=1e-9 * es)
+    np.testing.assert_allclose(H.dE_chain, fx["dE_chain"], rtol=0, atol=1e-9 * es)
+    assert H.accept_R == pytest.approx(float(fx["accept_R"]), abs=1e-15)
+    if not np.isnan(fx["accept_R_warm_up"]):
+        assert H.accept_R_warm_up == pytest.approx(float(fx["accept_R_warm_up"]), abs=1e-15)
+    assert H.N_total_steps == int(fx["N_total_steps"])
+    if nsave > 0:
+        np.testing.assert_array_equal(H.decision_chain, fx["decision_chain"])
+        np.testing.assert_array_equal(np.array([p.shape[0] for p in H.phi_q]), fx["phi_len"])
+        np.testing.assert_allclose(np.concatenate(H.phi_q, axis=0), fx["phi_q"], rtol=0, atol=1e-9 * qs)
+    H.compute_convergence_stats()
+    np.testing.assert_allclose(H.R_q, fx["R_q"], rtol=1e-7)
+    np.testing.assert_allclose(H.n_eff_q, fx["n_eff_q"], rtol=1e-5)
+
+
+def _teacher_forced(fx, dtype, kernel, always_accept):
+    """One single-iteration chain per (chain, iteration) of the oracle run."""
+    import samplers as S
+    tgt = O.MVNTarget(fx["q0"], fx["cov0"])
+    D, Nchain, Niter = int(fx["D"]), int(fx["Nchain"]), int(fx["Niter"])
+    dt = fx["dt"] if fx["dt"].ndim else float(fx["dt"])
+    R = O.gen_sample_random(D, tgt.V, tgt.dVdq, fx["q_start"], O.TapeDraws(flat_tape(fx)), Nchain, Niter,
+                            int(fx["thin_rate"]), int(fx["warm_up_num"]), dt, int(fx["L_low"]), int(fx["L_high"]),
+                            cov_p=fx["cov_p"], record=True)
+    B = Nchain * Niter
+    q_init = R.q_init.reshape(B, D)
+    p_tape = np.zeros((B, 2, D))
+    p_tape[:, 1] = R.p_tape[:, 1:].reshape(B, D)
+    L_tape = R.L_tape.reshape(B, 1)
+    u = R.u_tape.reshape(B, 1).copy()
+    if always_accept:
+        u[:] = 1e-300
+    cov_p = None if np.array_equal(fx["cov_p"], np.eye(D)) else fx["cov_p"]
+    H = S.HMC_sampler(D, None, None, Nchain=B, Niter=1, thin_rate=1, warm_up_num=0, cov_p=cov_p,
+                      sampler_type="Random", dt=dt, L_low=int(fx["L_low"]), L_high=int(fx["L_high"]), dtype=dtype,
+                      kernel=kernel, target=S.MVNSpec.from_cov(fx["q0"], fx["cov0"]),
+                      draws=dict(p_tape=p_tape, L_tape=L_tape, u_tape=u))
+    H.gen_sample(q_init, verbose=False)
+    return R, H, B
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small", "random_case2c_small"])
+def test_f32_teacher_forced_trajectories(name, kernel):
+    fx = load(name)
+    R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=True)
+    D = int(fx["D"])
+    got = H.q_chain[:, 1, :]
+    want = R.q_prop.reshape(B, D)
+    rel = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
+    assert rel.max() < 1e-5, "worst rel-L2 trajectory error %.3g" % rel.max()
+    # E_initial is stored at index 1 (warm_up_num = 0): float32 state, float64 scalar arithmetic
+    E_want = R.E_init_iter.reshape(B)
+    np.testing.assert_allclose(H.E_chain[:, 1, 0], E_want, rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small"])
+def test_f32_teacher_forced_decisions(name, kernel):
+    fx = load(name)
+    R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=False)
+    D = int(fx["D"])
+    want_dec = R.decision.reshape(B)
+    want_q = np.where(want_dec[:, None] == 1, R.q_prop.reshape(B, D), R.q_init.reshape(B, D))
+    got_q = H.q_chain[:, 1, :]
+    got_dec = np.linalg.norm(got_q - R.q_init.reshape(B, D), axis=1) > 0       # moved <=> accepted
+    dE = R.dE_iter.reshape(B)
+    lnu = np.log(R.u_tape.reshape(B))
+    margin = np.abs(lnu + dE)
+    near_tie = (dE >= 0) & (margin < 1e-3 * np.maximum(1.0, np.abs(R.E_init_iter.reshape(B))))
+    differ = got_dec != (want_dec == 1)
+    assert not np.any(differ & ~near_tie), "decision flips away from ties: %d" % int(np.sum(differ & ~near_tie))
+    assert near_tie.mean() < 0.02
+    ok = ~differ
+    rel = np.linalg.norm(got_q[ok] - want_q[ok], axis=1) / np.maximum(np.linalg.norm(want_q[ok], axis=1), 1e-30)
+    assert rel.max() < 1e-5
+
+
+def test_f64_long_trajectories_case3d():
+    """L in [50,200): float32 cannot hold rel 1e-5 here, the float64 instantiation must."""
+    fx = load("random_case3d_small")
+    R, H, B = _teacher_forced(fx, "float64", "generic", always_accept=True)
+    want = R.q_prop.reshape(B, int(fx["D"]))
+    rel = np.linalg.norm(H.q_chain[:, 1, :] - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert rel.max() < 1e-10
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_philox_path_matches_oracle_on_device_draws(dtype):
+    """Free-running with the kernel's own Philox draws: the oracle is fed exactly those draws
+    (hmc_philox_draws) and must produce the same stream (float64) / the same statistics (float32)."""
+    import torch
+    import hmc_b200_lib as L
+    import samplers as S
+    D, rho, Nchain, Niter, warm, thin = 10, 0.9, 64, 50, 10, 2
+    tgt = O.MVNTarget(np.zeros(D), O.equicorrelated_cov(D, rho))
+    rng = np.random.RandomState(3)
+    q_start = rng.standard_normal((Nchain, D)) * 1.5
+    seed, id0 = 1234, 1000
+    H = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=Nchain, Niter=Niter, thin_rate=thin, warm_up_num=warm,
+                      sampler_type="Random", dt=0.1, L_low=5, L_high=20, dtype=dtype, kernel="generic", seed=seed,
+                      chain_id0=id0)
+    H.gen_sample(q_start, verbose=False)
+    lib = L.load()
+    p = torch.zeros((Nchain, Niter + 1, D), dtype=torch.float64, device="cuda")
+    Lt = torch.zeros((Nchain, Niter), dtype=torch.int32, device="cuda")
+    u = torch.zeros((Nchain, Niter), dtype=torch.float64, device="cuda")
+    L.check(lib.hmc_philox_draws(seed, id0, Nchain, Niter, D, 5, 20, L.ptr(p), L.ptr(Lt), L.ptr(u), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    fx = dict(Nchain=Nchain, Niter=Niter, p_tape=p.cpu().numpy(), L_tape=Lt.cpu().numpy(), u_tape=u.cpu().numpy())
+    assert fx["L_tape"].min() >= 5 and fx["L_tape"].max() <= 19
+    assert abs(fx["p_tape"].mean()) < 0.02 and abs(fx["p_tape"].std() - 1) < 0.02
+    assert 0 < fx["u_tape"].min() and fx["u_tape"].max() < 1
+    R = O.gen_sample_random(D, tgt.V, tgt.dVdq, q_start, O.TapeDraws(flat_tape(fx)), Nchain, Niter, thin, warm, 0.1, 5, 20)
+    if dtype == "float64":
+        np.testing.assert_allclose(H.q_chain, R.q_chain, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(H.E_chain, R.E_chain, rtol=0, atol=1e-8)
+        assert H.accept_R == R.accept_R
+    else:
+        assert abs(H.accept_R - R.accept_R) < 0.01
+        same = np.linalg.norm(H.q_chain[:, 1] - R.q_chain[:, 1], axis=1) / np.linalg.norm(R.q_chain[:, 1], axis=1)
+        assert same.max() < 1e-4      # first stored sample: still on the same trajectory
+
+
+def test_sharding_invariance_and_iteration_blocks():
+    """Chains split over two 'devices' (chain_id0 offsets) and iterations split over several launches give
+    bit-identical streams: Philox is keyed by global chain id and iteration."""
+    import samplers as S
+    D, Nchain, Niter = 6, 40, 30
+    tgt = O.MVNTarget(np.zeros(D), O.equicorrelated_cov(D, 0.5))
+    q_start = np.random.RandomState(0).standard_normal((Nchain, D))
+    kw = dict(Niter=Niter, thin_rate=1, warm_up_num=5, sampler_type="Random", dt=0.2, L_low=3, L_high=9,
+              dtype="float32", kernel="generic", seed=99, target=S.MVNSpec.from_cov(np.zeros(D), tgt.cov0))
+    full = S.HMC_sampler(D, None, None, Nchain=Nchain, **kw)
+    full.gen_sample(q_start, verbose=False)
+    a = S.HMC_sampler(D, None, None, Nchain=16, chain_id0=0, iter_block=7, **kw)
+    a.gen_sample(q_start[:16], verbose=False)
+    b = S.HMC_sampler(D, None, None, Nchain=24, chain_id0=16, iter_block=11, **kw)
+    b.gen_sample(q_start[16:], verbose=False)
+    np.testing.assert_array_equal(np.concatenate([a.q_chain, b.q_chain]), full.q_chain)
+    np.testing.assert_array_equal(np.concatenate([a.E_chain, b.E_chain]), full.E_chain)
+    np.testing.assert_array_equal(np.concatenate([a.dE_chain, b.dE_chain]), full.dE_chain)
+
+
+def test_fixed_sampler_is_random_with_constant_L():
+    import samplers as S
+    D, Nchain, Niter = 4, 8, 20
+    tgt = O.MVNTarget(np.zeros(D), np.eye(D))
+    q_start = np.random.RandomState(1).standard_normal((Nchain, D))
+    H = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=Nchain, Niter=Niter, sampler_type="Fixed", L=7, dt=0.1,
+                      dtype="float64", kernel="generic", seed=5)
+    H.gen_sample(q_start, verbose=False)
+    assert H.sum_L == 7 * Nchain * Niter
+    assert H.N_total_steps == Nchain * (1 + 2 * Niter) + D * 49 * Nchain * Niter
+
+
+def test_target_extraction_and_errors():
+    import samplers as S
+    import hmc_b200_lib as L
+    D = 5
+    rng = np.random.RandomState(2)
+    A = rng.standard_normal((D, D))
+    cov = A @ A.T + D * np.eye(D)
+    q0 = rng.standard_normal(D)
+    tgt = O.MVNTarget(q0, cov)
+    spec = S.extract_mvn_target(D, tgt.V, tgt.dVdq)
+    np.testing.assert_allclose(spec.P, tgt.inv_cov0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(spec.mu, q0, rtol=1e-9, atol=1e-12)
+    assert spec.const == pytest.approx(tgt.const, rel=1e-12)
+    with pytest.raises(NotImplementedError):
+        S.extract_mvn_target(D, lambda q: np.sum(q ** 4), lambda q: 4 * q ** 3)
+    with pytest.raises(AssertionError):                                    # samplers.py:332
+        S.HMC_sampler(D, tgt.V, tgt.dVdq, sampler_type="Random", L_low=2, L_high=5)
+    H = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=3, Niter=5, sampler_type="Random", L_low=2, L_high=5, dt=0.1)
+    with pytest.raises(AssertionError):                                    # samplers.py:396
+        H.gen_sample(np.zeros((4, D)), verbose=False)
+    bad = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=3, Niter=5, sampler_type="Random", L_low=5, L_high=5, dt=0.1)
+    with pytest.raises(L.HMCError) as ei:
+        bad.gen_sample(np.zeros((3, D)), verbose=False)
+    assert ei.value.code == L.HMC_E_BADARG

@@ -1,0 +1,188 @@
+// Diagnostics as HBM-bound reductions over the sample stream q_chain[Nchain][L_chain][D]:
+//   hmc_diag_moments   -- split-chain mean / ddof=1 std  (utils.convergence_stats, /root/reference/utils.py:88-118)
+//   hmc_diag_variogram -- variogram numerators for a chunk of lags (utils.variogram, utils.py:161-179)
+// One thread owns one (split chain, dimension) time series at a time; consecutive threads own consecutive
+// dimensions, so every load of a warp is one contiguous row segment.  Per-thread partials are float64,
+// combined per block in shared memory and added to the output with one float64 atomic per (block, value).
+#include "hmc_common.cuh"
+
+namespace {
+
+constexpr int kDiagThreads = 256;
+
+// `q` points at sample 0 of chain 0; `stride_chain` elements between chains; a split chain s = 2*m + h is
+// samples [h*n, h*n + n) of chain m (utils.py:102-104).
+template <typename T>
+__global__ void __launch_bounds__(kDiagThreads) diag_moments_kernel(const T* __restrict__ q, long Nchain, long n, int D,
+                                                                    long stride_chain, int spb, double* __restrict__ out) {
+    extern __shared__ double sm[];   // [3][D]
+    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int d = threadIdx.x % D;
+    const int sl = threadIdx.x / D;
+    double s_std = 0.0, s_mean = 0.0, s_mean2 = 0.0;
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            const double x0 = (double)x[0];
+            double a = 0.0, b = 0.0;
+            long i = 0;
+            for (; i + 4 <= n; i += 4) {
+                const double v0 = (double)x[(i + 0) * D] - x0, v1 = (double)x[(i + 1) * D] - x0;
+                const double v2 = (double)x[(i + 2) * D] - x0, v3 = (double)x[(i + 3) * D] - x0;
+                a += (v0 + v1) + (v2 + v3);
+                b += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+            }
+            for (; i < n; ++i) { const double v = (double)x[i * D] - x0; a += v; b += v * v; }
+            const double mean_s = a / (double)n;
+            double var = (b - (double)n * mean_s * mean_s) / (double)(n - 1);   // ddof = 1 (utils.py:111)
+            if (var < 0.0) var = 0.0;
+            const double mean = mean_s + x0;
+            s_std += sqrt(var);
+            s_mean += mean;
+            s_mean2 += mean * mean;
+        }
+        atomicAdd(&sm[d], s_std);
+        atomicAdd(&sm[D + d], s_mean);
+        atomicAdd(&sm[2 * D + d], s_mean2);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+}
+
+// Lags t = lag0 + k, k < NL.  For every i the pair (x[i], x[i - lag0 - k]) contributes (x[i]-x[i-lag0-k])^2.
+// The last NL delayed values live in a register window addressed with compile-time indices (the time loop is
+// unrolled by NL); float partial sums are flushed into float64 every NL steps.
+template <typename T, int NL>
+__global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* __restrict__ q, long Nchain, long n, int D,
+                                                                      long stride_chain, int spb, int lag0, int nlags,
+                                                                      double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NL][D]
+    for (int t = threadIdx.x; t < NL * D; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int d = threadIdx.x % D;
+    const int sl = threadIdx.x / D;
+    double dacc[NL];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) dacc[k] = 0.0;
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            T w[NL];         // w[(i - lag0) % NL] = x[i - lag0]
+            float acc[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) { w[k] = T(0); acc[k] = 0.f; }
+            long i0 = lag0;
+            // first block: entry k is valid only once i - lag0 - k >= 0, i.e. k <= r (compile-time)
+            {
+#pragma unroll
+                for (int r = 0; r < NL; ++r) {
+                    const long i = i0 + r;
+                    if (i < n) {
+                        const T xa = x[i * D];
+                        w[r] = x[(i - lag0) * D];
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) {
+                            if (k <= r) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+                i0 += NL;
+            }
+            for (; i0 + NL <= n; i0 += NL) {        // steady state, no conditions
+#pragma unroll
+                for (int r = 0; r < NL; ++r) {
+                    const long i = i0 + r;
+                    const T xa = x[i * D];
+                    w[r] = x[(i - lag0) * D];
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                }
+#pragma unroll
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+            }
+            if (i0 < n) {                            // tail
+#pragma unroll
+                for (int r = 0; r < NL; ++r) {
+                    const long i = i0 + r;
+                    if (i < n) {
+                        const T xa = x[i * D];
+                        w[r] = x[(i - lag0) * D];
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], dacc[k]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+}
+
+int grid_for(long nseries, int spb) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long want = (nseries + spb - 1) / spb;
+    long cap = (long)sms * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+#define HMC_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            hmc_set_error(__VA_ARGS__);   \
+            return HMC_E_BADARG;          \
+        }                                 \
+    } while (0)
+
+extern "C" int hmc_diag_moments(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
+                                double* out3xD, void* cuda_stream) {
+    HMC_REQUIRE(q && out3xD, "NULL buffer");
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kDiagThreads, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kDiagThreads);
+    HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int spb = kDiagThreads / D;
+    const int grid = grid_for(2 * Nchain, spb);
+    const size_t smem = sizeof(double) * 3 * D;
+    HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, smem, stream));
+    if (dtype == HMC_F32)
+        diag_moments_kernel<float><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, out3xD);
+    else
+        diag_moments_kernel<double><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, out3xD);
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
+extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
+                                  int32_t lag0, int32_t nlags, double* out, void* cuda_stream) {
+    constexpr int NL = 32;
+    HMC_REQUIRE(q && out, "NULL buffer");
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kDiagThreads, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kDiagThreads);
+    HMC_REQUIRE(lag0 >= 1 && nlags >= 1 && nlags <= NL, "need lag0 >= 1 and 1 <= nlags <= %d", NL);
+    HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int spb = kDiagThreads / D;
+    const int grid = grid_for(2 * Nchain, spb);
+    const size_t smem = sizeof(double) * NL * D;
+    HMC_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * nlags * D, stream));
+    if (dtype == HMC_F32) {
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_variogram_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);
+    } else {
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_variogram_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);
+    }
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}

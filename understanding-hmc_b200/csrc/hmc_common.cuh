@@ -1,0 +1,86 @@
+// Shared device helpers: Philox4x32-10, Box-Muller, draw keying, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/hmc_b200.h"
+
+#define HMC_FULL_MASK 0xffffffffu
+
+void hmc_set_error(const char* fmt, ...);
+#define HMC_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            hmc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return HMC_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: every draw is a pure function of
+// (seed, global chain id, iteration, slot, stream) so chains can be sharded over any number of GPUs.
+// ---------------------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+enum { HMC_STREAM_MOMENTUM = 0, HMC_STREAM_SCALAR = 1, HMC_STREAM_NUTS = 2 };
+
+// 4 standard normals for dims 4*slot .. 4*slot+3 of (chain, iteration): float32 Box-Muller.
+__device__ __forceinline__ float4 hmc_normal4(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t slot) {
+    Philox4 r = philox4x32_10((uint32_t)chain, iter, slot, HMC_STREAM_MOMENTUM | ((uint32_t)(chain >> 32) << 8),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float S = 2.3283064365386963e-10f;  // 2^-32
+    float u1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (0,1), 24 bits
+    float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    float r1 = sqrtf(-2.0f * logf(u1));
+    float r2 = sqrtf(-2.0f * logf(u2));
+    float s1, c1, s2, c2;
+    sincospif(2.0f * ((float)r.y * S), &s1, &c1);
+    sincospif(2.0f * ((float)r.w * S), &s2, &c2);
+    return make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
+}
+
+// Trajectory length in {L_low .. L_high-1} and acceptance uniform in (0,1) for (chain, iteration).
+__device__ __forceinline__ void hmc_scalar_draws(uint64_t seed, uint64_t chain, uint32_t iter, int L_low, int L_high,
+                                                 int* L, double* u) {
+    Philox4 r = philox4x32_10((uint32_t)chain, iter, 0u, HMC_STREAM_SCALAR | ((uint32_t)(chain >> 32) << 8),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    *L = L_low + (int)__umulhi(r.x, (uint32_t)(L_high - L_low));
+    *u = ((double)r.y + 0.5) * 2.3283064365386963e-10;
+}
+
+// NUTS per-chain stream: draw number n of iteration iter -> (coin, uniform).
+__device__ __forceinline__ void hmc_nuts_draw(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t n, int* coin,
+                                              double* u) {
+    Philox4 r = philox4x32_10((uint32_t)chain, iter, n, HMC_STREAM_NUTS | ((uint32_t)(chain >> 32) << 8),
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+    *coin = (int)(r.x >> 31);
+    *u = ((double)r.y + 0.5) * 2.3283064365386963e-10;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HMC_FULL_MASK, v, o);
+    return v;
+}

@@ -1,0 +1,262 @@
+// Design probes for the fused trajectory kernel (not part of the library): measures, on the box, the FP32 FMA
+// peak and the achieved FMA rate of candidate inner loops (operands in shared memory, accumulators in
+// registers) so that the register-tile shape is chosen from measurements, not guesses.
+//   build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo microbench.cu -o ../../gpurun_out/microbench
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+    unsigned long long D = *reinterpret_cast<unsigned long long*>(&d);
+    const unsigned long long A = *reinterpret_cast<const unsigned long long*>(&a);
+    const unsigned long long B = *reinterpret_cast<const unsigned long long*>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(D) : "l"(A), "l"(B));
+    d = *reinterpret_cast<float2*>(&D);
+}
+
+// ---- (0) raw FMA peak ------------------------------------------------------------------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(512) peak_kernel(float* out, int iters) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    float2 a = make_float2(0.999f, 0.998f), b = make_float2(0.001f, 0.002f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (PACKED) { float2 t = acc[i]; acc[i] = b; ffma2(acc[i], a, t); }
+            else { acc[i].x = fmaf(a.x, acc[i].x, b.x); acc[i].y = fmaf(a.y, acc[i].y, b.y); }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- (A) warp tile: 6 chain-groups x 5 dim-groups per warp, thread tile 2 chains x 20 dims -------------------
+// P [K][100] plain in smem (shared by all warps); per-warp q tile [K][6][4] = (q0,q0,q1,q1) duplicated.
+template <bool PACKED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) warp_tile_kernel(float* out, int steps) {
+    constexpr int K = 100, D = 100;
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;                                   // K * D
+    float* Q = sm + K * D + (threadIdx.x >> 5) * (K * 24);
+    for (int t = threadIdx.x; t < K * D; t += blockDim.x) P[t] = 1e-3f * ((t * 7) % 13 - 6);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < K * 24; t += 32) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncthreads();
+    const int cg = lane / 5, dg = lane % 5;
+    const bool active = lane < 30;
+    float2 acc[2][10];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc[c][j] = make_float2(0.f, 0.f);
+    const float* qp = Q + (active ? cg : 0) * 4;
+    const float* pp = P + (active ? dg : 0) * 20;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float4 qv = *reinterpret_cast<const float4*>(qp + k * 24);
+            float4 pv[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) pv[i] = *reinterpret_cast<const float4*>(pp + k * D + 4 * i);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (PACKED) {
+                    ffma2(acc[0][2 * i], make_float2(qv.x, qv.y), make_float2(pv[i].x, pv[i].y));
+                    ffma2(acc[0][2 * i + 1], make_float2(qv.x, qv.y), make_float2(pv[i].z, pv[i].w));
+                    ffma2(acc[1][2 * i], make_float2(qv.z, qv.w), make_float2(pv[i].x, pv[i].y));
+                    ffma2(acc[1][2 * i + 1], make_float2(qv.z, qv.w), make_float2(pv[i].z, pv[i].w));
+                } else {
+                    acc[0][2 * i].x = fmaf(qv.x, pv[i].x, acc[0][2 * i].x); acc[0][2 * i].y = fmaf(qv.x, pv[i].y, acc[0][2 * i].y);
+                    acc[0][2 * i + 1].x = fmaf(qv.x, pv[i].z, acc[0][2 * i + 1].x); acc[0][2 * i + 1].y = fmaf(qv.x, pv[i].w, acc[0][2 * i + 1].y);
+                    acc[1][2 * i].x = fmaf(qv.z, pv[i].x, acc[1][2 * i].x); acc[1][2 * i].y = fmaf(qv.z, pv[i].y, acc[1][2 * i].y);
+                    acc[1][2 * i + 1].x = fmaf(qv.z, pv[i].z, acc[1][2 * i + 1].x); acc[1][2 * i + 1].y = fmaf(qv.z, pv[i].w, acc[1][2 * i + 1].y);
+                }
+            }
+        }
+        // feed something back so the loop is not hoisted
+        if (acc[0][0].x == 123.456f) Q[lane] = acc[1][3].y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s += acc[c][j].x + acc[c][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- (B) warp tile variant: 3 chain-groups x 10 dim-groups, thread tile 4 chains x 10 dims --------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) warp_tile_b_kernel(float* out, int steps) {
+    constexpr int K = 100, D = 100;
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;
+    float* Q = sm + K * D + (threadIdx.x >> 5) * (K * 24);   // [K][3 cg][8] = 4 chains duplicated
+    for (int t = threadIdx.x; t < K * D; t += blockDim.x) P[t] = 1e-3f * ((t * 7) % 13 - 6);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < K * 24; t += 32) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncthreads();
+    const bool active = lane < 30;
+    const int cg = active ? lane / 10 : 0, dg = active ? lane % 10 : 0;
+    float2 acc[4][5];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[c][j] = make_float2(0.f, 0.f);
+    const float* qp = Q + cg * 8;
+    const float* pp = P + dg * 10;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float4 qa = *reinterpret_cast<const float4*>(qp + k * 24);
+            const float4 qb = *reinterpret_cast<const float4*>(qp + k * 24 + 4);
+            float2 pv[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) pv[i] = *reinterpret_cast<const float2*>(pp + k * D + 2 * i);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                ffma2(acc[0][i], make_float2(qa.x, qa.y), pv[i]);
+                ffma2(acc[1][i], make_float2(qa.z, qa.w), pv[i]);
+                ffma2(acc[2][i], make_float2(qb.x, qb.y), pv[i]);
+                ffma2(acc[3][i], make_float2(qb.z, qb.w), pv[i]);
+            }
+        }
+        if (acc[0][0].x == 123.456f) Q[lane] = acc[1][3].y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s += acc[c][j].x + acc[c][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- (C) CTA tile: 8 chains x 4 dims per thread, pairs along chains, P duplicated in smem ---------------------
+// q tile [K][2][NCG][4], Pdup [K][2][32 dg slots][4]; warp = 4 cg x 8 dg.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cta_tile_kernel(float* out, int steps) {
+    constexpr int K = 100, NCG = 20, NDGS = 32;
+    extern __shared__ __align__(16) float sm[];
+    float* Pd = sm;                          // K * 2 * NDGS * 4
+    float* Q = sm + K * 2 * NDGS * 4;        // K * 2 * NCG * 4
+    for (int t = threadIdx.x; t < K * 2 * NDGS * 4; t += blockDim.x) Pd[t] = 1e-3f * ((t * 7) % 13 - 6);
+    for (int t = threadIdx.x; t < K * 2 * NCG * 4; t += blockDim.x) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = (warp % 5) * 4 + (lane >> 3);
+    const int dg = (warp / 5) * 8 + (lane & 7);
+    float2 acc[4][4];    // [chain pair][dim]
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
+    const float* qp = Q + cg * 4;
+    const float* pp = Pd + dg * 4;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const float4 q0 = *reinterpret_cast<const float4*>(qp + (k * 2 + 0) * NCG * 4);
+            const float4 q1 = *reinterpret_cast<const float4*>(qp + (k * 2 + 1) * NCG * 4);
+            const float4 p0 = *reinterpret_cast<const float4*>(pp + (k * 2 + 0) * NDGS * 4);
+            const float4 p1 = *reinterpret_cast<const float4*>(pp + (k * 2 + 1) * NDGS * 4);
+            const float2 qq[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+            const float2 pd[4] = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y), make_float2(p1.z, p1.w)};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ffma2(acc[c][j], qq[c], pd[j]);
+        }
+        if (acc[0][0].x == 123.456f) Q[lane] = acc[1][3].y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[c][j].x + acc[c][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+double time_ms(F launch, int reps = 3) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        CK(cudaEventRecord(e0));
+        launch();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return best;
+}
+
+int main() {
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    int clk = 0;
+    CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0));
+    printf("SMs %d, max clock %d kHz, nominal FP32 peak %.2f TFLOP/s\n", sms, clk, 2.0 * 128 * sms * clk * 1e3 / 1e12);
+    float* out;
+    CK(cudaMalloc(&out, sizeof(float) * sms * 8 * 1024));
+    {
+        const int iters = 20000, blocks = sms * 4, threads = 512;
+        double ms = time_ms([&] { peak_kernel<false><<<blocks, threads>>>(out, iters); });
+        printf("peak FFMA   : %.2f TFLOP/s\n", 2.0 * 32 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+        ms = time_ms([&] { peak_kernel<true><<<blocks, threads>>>(out, iters); });
+        printf("peak FFMA2  : %.2f TFLOP/s\n", 2.0 * 32 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+    }
+    const int steps = 2000;
+    {
+        constexpr int W = 16;
+        const size_t smem = sizeof(float) * (100 * 100 + W * 100 * 24);
+        auto k1 = warp_tile_kernel<true, W>;
+        auto k2 = warp_tile_kernel<false, W>;
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double flop = 2.0 * 100 * 100 * 12.0 * W * sms * steps;   // 12 chains per warp
+        double ms = time_ms([&] { k1<<<sms, W * 32, smem>>>(out, steps); });
+        printf("(A) warp tile 6x5 (2x20) FFMA2, %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+        ms = time_ms([&] { k2<<<sms, W * 32, smem>>>(out, steps); });
+        printf("(A) warp tile 6x5 (2x20) FFMA , %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+    }
+    {
+        constexpr int W = 12;
+        const size_t smem = sizeof(float) * (100 * 100 + W * 100 * 24);
+        auto k1 = warp_tile_kernel<true, W>;
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double flop = 2.0 * 100 * 100 * 12.0 * W * sms * steps;
+        double ms = time_ms([&] { k1<<<sms, W * 32, smem>>>(out, steps); });
+        printf("(A) warp tile 6x5 (2x20) FFMA2, %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+    }
+    {
+        constexpr int W = 16;
+        const size_t smem = sizeof(float) * (100 * 100 + W * 100 * 24);
+        auto k1 = warp_tile_b_kernel<W>;
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double flop = 2.0 * 100 * 100 * 12.0 * W * sms * steps;
+        double ms = time_ms([&] { k1<<<sms, W * 32, smem>>>(out, steps); });
+        printf("(B) warp tile 3x10 (4x10) FFMA2, %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+    }
+    {
+        constexpr int W = 15;   // 5 cg-blocks x 3 dg-blocks (96 of 100 dims; the probe ignores the last dim group)
+        const size_t smem = sizeof(float) * (100 * 2 * 32 * 4 + 100 * 2 * 20 * 4);
+        auto k1 = cta_tile_kernel<W>;
+        CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double flop = 2.0 * 100 * 96 * 160.0 * sms * steps;
+        double ms = time_ms([&] { k1<<<sms, W * 32, smem>>>(out, steps); });
+        printf("(C) CTA tile 8x4 Pdup FFMA2, %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaFree(out));
+    return 0;
+}

@@ -1,0 +1,229 @@
+// Generic random-trajectory-length HMC kernel: ONE WARP PER CHAIN, float or double, D <= 1024,
+// dense momentum metric and per-dimension dt supported.  This is the parity workhorse (its float64
+// instantiation is compared with the float64 oracle to ~1e-10) and the path for everything the FFMA2
+// fast kernel (random_fast.cu) does not cover.  It follows HMC_sampler.gen_sample_random
+// (/root/reference/samplers.py:387-491) statement by statement; lane `l` owns dimensions l, l+32, ...
+#include "hmc_common.cuh"
+
+namespace {
+
+// y = M x for a D x D matrix given by its transpose Mt[k][j] (row pitch Dp); x, y distributed over the warp
+// (lane l owns j = l, l+32, ...).  x is staged in a per-warp shared buffer and read back as a broadcast.
+template <typename T, int NJ>
+__device__ __forceinline__ void matvec_t(const T* __restrict__ Mt, int D, int Dp, const T (&x)[NJ], T (&y)[NJ],
+                                         int lane, T* __restrict__ xs) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) { y[i] = T(0); const int j = lane + 32 * i; if (j < D) xs[j] = x[i]; }
+    __syncwarp();
+#pragma unroll 2
+    for (int k = 0; k < D; ++k) {
+        const T xk = xs[k];
+        const T* row = Mt + (size_t)k * Dp;
+#pragma unroll
+        for (int i2 = 0; i2 < NJ; ++i2) {
+            const int j = lane + 32 * i2;
+            if (j < D) y[i2] = fma(row[j], xk, y[i2]);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T, int NJ>
+__device__ __forceinline__ double dot_warp(const T (&a)[NJ], const T (&b)[NJ]) {
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) s = fma(a[i], b[i], s);
+    return warp_sum<double>((double)s);
+}
+
+template <typename T, int NJ>
+__global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args a, int smem_mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = a.target.D, Dp = a.target.D_pad;
+    const T* Ft = (const T*)a.target.Ft;
+    const T* Pt = (const T*)a.target.Pt;
+    const T* Mit = (const T*)a.target.Mit;
+    const T* Lct = (const T*)a.target.Lct;
+    T* xs = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * Dp;   // per-warp staging vector
+    {   // stage the matrices that fit into shared memory (decided by the host)
+        T* s = (T*)smem_raw + (size_t)(blockDim.x >> 5) * Dp;
+        const int n = D * Dp;
+        if (smem_mask & 1) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Ft[t]; Ft = s; s += n; }
+        if ((smem_mask & 2) && Pt) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Pt[t]; Pt = s; s += n; }
+        if ((smem_mask & 4) && Mit) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Mit[t]; Mit = s; s += n; }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const long m = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= a.Nchain) return;
+    const uint64_t gid = (uint64_t)(a.chain_id0 + m);
+    const T* mu_g = (const T*)a.target.mu;
+    const T* dt_g = (const T*)a.target.dt;
+    T* q_chain = (T*)a.q_chain;
+    const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;   // samplers.py:31
+
+    T q[NJ], p[NJ], f[NJ], d[NJ], mu[NJ], dt[NJ], tmp[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+        const int j = lane + 32 * i;
+        mu[i] = (j < D) ? mu_g[j] : T(0);
+        dt[i] = (j < D) ? dt_g[j] : T(0);
+        q[i] = T(0); p[i] = T(0); f[i] = T(0);
+    }
+
+    auto draw_p = [&](int iter) {
+        if (a.p_tape) {
+            const double* src = a.p_tape + ((size_t)m * (a.Niter + 1) + iter) * D;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; p[i] = (j < D) ? (T)src[j] : T(0); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+                const int j = lane + 32 * i;
+                if (j < D) {
+                    float4 z = hmc_normal4(a.seed, gid, (uint32_t)iter, (uint32_t)(j >> 2));
+                    const int r = j & 3;
+                    p[i] = (T)(r == 0 ? z.x : r == 1 ? z.y : r == 2 ? z.z : z.w);
+                } else p[i] = T(0);
+            }
+            if (Lct) {   // p = Lc z ~ N(0, cov_p)   (samplers.py:829)
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) tmp[i] = p[i];
+                matvec_t<T, NJ>(Lct, D, Dp, tmp, p, lane, xs);
+            }
+        }
+    };
+    auto force = [&]() {          // f = F (q - mu)
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) d[i] = q[i] - mu[i];
+        matvec_t<T, NJ>(Ft, D, Dp, d, f, lane, xs);
+    };
+    auto potential = [&]() -> double {   // V(q); requires d, f current for q
+        if (Pt) { matvec_t<T, NJ>(Pt, D, Dp, d, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(d, tmp) + a.target.v_const; }
+        return 0.5 * dot_warp<T, NJ>(d, f) + a.target.v_const;
+    };
+    auto kinetic = [&]() -> double {
+        if (Mit) { matvec_t<T, NJ>(Mit, D, Dp, p, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(p, tmp); }
+        return 0.5 * dot_warp<T, NJ>(p, p);
+    };
+
+    double E_previous;
+    unsigned long long acc_warm = 0, acc_post = 0, sumL = 0, sumL2 = 0;
+    if (a.iter_begin == 0) {                                            // samplers.py:413-420
+        const T* qs = (const T*)a.q_start + (size_t)m * D;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
+        draw_p(0);
+        force();
+        const double E0 = potential() + kinetic();
+        if (lane == 0) { a.E_chain[(size_t)m * Lc] = E0; a.dE_chain[(size_t)m * Lc] = 0.0; }
+        E_previous = E0;
+        if (a.decision_chain && gid == 0 && lane == 0) a.decision_chain[a.N_save_chain0] = 0;
+    } else {
+        const T* qs = (const T*)a.state_q + (size_t)m * D;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) q[i] = qs[j]; }
+        E_previous = a.state_eprev[m];
+    }
+
+    T q_init[NJ];
+    for (int it = a.iter_begin + 1; it <= a.iter_end; ++it) {           // samplers.py:428
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) q_init[i] = q[i];
+        draw_p(it);                                                     // samplers.py:431
+        force();
+        const double E_initial = potential() + kinetic();               // samplers.py:434
+        const bool keep = it >= a.warm_up_num;
+        const long idx = keep ? (it - a.warm_up_num) / a.thin_rate : 0;
+        if (keep && lane == 0) {                                        // samplers.py:436-438
+            a.E_chain[(size_t)m * Lc + idx] = E_initial;
+            a.dE_chain[(size_t)m * Lc + idx] = E_initial - E_previous;
+        }
+        int L; double u;
+        if (a.L_tape) { L = a.L_tape[(size_t)m * a.Niter + it - 1]; u = a.u_tape[(size_t)m * a.Niter + it - 1]; }
+        else hmc_scalar_draws(a.seed, gid, (uint32_t)it, a.L_low, a.L_high, &L, &u);
+        sumL += L; sumL2 += (unsigned long long)L * L;
+        const bool trace = a.phi_q && gid == 0 && it <= a.N_save_chain0;
+        double* phi = trace ? a.phi_q + (size_t)(it - 1) * a.L_high * 2 : nullptr;
+        if (trace) { if (lane < 2 && lane < D) phi[lane] = (double)q[0]; if (lane == 0) a.phi_len[it - 1] = L + 1; }
+        for (int l = 1; l <= L; ++l) {                                  // samplers.py:448-452, leap_frog :831-839
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) {
+                p[i] = p[i] - dt[i] * f[i] / T(2);
+                q[i] = q[i] + dt[i] * p[i];
+            }
+            force();
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) p[i] = p[i] - dt[i] * f[i] / T(2);
+            if (trace && lane < 2 && lane < D) phi[2 * l + lane] = (double)q[0];
+        }
+        const double E_final = potential() + kinetic();                 // samplers.py:455
+        const double dE = E_final - E_initial;
+        E_previous = E_initial;                                         // samplers.py:460
+        const double lnu = log(u);
+        const bool accepted = (dE < 0) || (lnu < -dE);                  // samplers.py:462
+        if (accepted) {
+            if (trace && lane == 0) a.decision_chain[it - 1] = 1;
+            if (keep) acc_post++; else acc_warm++;
+        } else {
+            if (trace && lane == 0) a.decision_chain[it - 1] = 0;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) q[i] = q_init[i];
+        }
+        if (keep) {                                                     // samplers.py:465-471 (Q4: negative-index writes skipped)
+            T* dst = q_chain + ((size_t)m * Lc + idx) * D;
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) dst[j] = q[i]; }
+        }
+    }
+    {
+        T* qs = (T*)a.state_q + (size_t)m * D;
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) qs[j] = q[i]; }
+        if (lane == 0) {
+            a.state_eprev[m] = E_previous;
+            if (a.counters) {
+                atomicAdd(a.counters + 0, acc_warm);
+                atomicAdd(a.counters + 1, acc_post);
+                atomicAdd(a.counters + 2, sumL);
+                atomicAdd(a.counters + 3, sumL2);
+            }
+        }
+    }
+}
+
+template <typename T, int NJ>
+int launch_generic(const hmc_random_args& a, cudaStream_t stream) {
+    const int warps = 4;
+    const int blocks = (a.Nchain + warps - 1) / warps;
+    const size_t mat = (size_t)a.target.D * a.target.D_pad * sizeof(T);
+    int mask = 0;
+    size_t smem = (size_t)warps * a.target.D_pad * sizeof(T);
+    const size_t budget = 200 * 1024;
+    if (smem + mat <= budget) { mask |= 1; smem += mat; }
+    if (a.target.Pt && smem + mat <= budget) { mask |= 2; smem += mat; }
+    if (a.target.Mit && smem + mat <= budget) { mask |= 4; smem += mat; }
+    auto kern = hmc_random_generic_kernel<T, NJ>;
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, warps * 32, smem, stream>>>(a, mask);
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
+template <typename T>
+int dispatch_generic(const hmc_random_args& a, cudaStream_t stream) {
+    const int D = a.target.D;
+    if (D <= 32) return launch_generic<T, 1>(a, stream);
+    if (D <= 128) return launch_generic<T, 4>(a, stream);
+    if (D <= 256) return launch_generic<T, 8>(a, stream);
+    if (D <= 1024) return launch_generic<T, 32>(a, stream);
+    hmc_set_error("generic kernel supports D <= 1024 (got %d)", D);
+    return HMC_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+int hmc_random_run_generic(const hmc_random_args& a, cudaStream_t stream) {
+    if (a.dtype == HMC_F32) return dispatch_generic<float>(a, stream);
+    return dispatch_generic<double>(a, stream);
+}
