@@ -182,6 +182,99 @@ __global__ void __launch_bounds__(WARPS * 32) cta_tile_kernel(float* out, int st
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- (D) lane-owns-chains: thread = 2 chains (one FFMA2 pair) x all dims in slices of TN; P from the constant
+// bank through uniform registers (LDCU + FFMA2 with a scalar UR operand); q tile per warp [K][66] in smem.
+__constant__ float Pc[100 * 100];
+template <int TN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) lane_chain_kernel(float* out, int steps) {
+    constexpr int K = 100, D = 100, QS = 66;
+    extern __shared__ __align__(16) float sm[];
+    float* Q = sm + (threadIdx.x >> 5) * (K * QS);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < K * QS; t += 32) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncwarp();
+    float2 tot = make_float2(0.f, 0.f);
+    const float* qp = Q + 2 * lane;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll 1
+        for (int sl = 0; sl < D / TN; ++sl) {
+            float2 acc[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float2 qv = *reinterpret_cast<const float2*>(qp + k * QS);
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const float pj = Pc[k * D + sl * TN + j];
+                    ffma2(acc[j], qv, make_float2(pj, pj));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { tot.x += acc[j].x; tot.y += acc[j].y; }
+        }
+        if (tot.x == 123.456f) Q[lane] = tot.y;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = tot.x + tot.y;
+}
+
+
+// ---- (E) generic per-warp register tile: thread = TM chains (FFMA2 pairs along chains) x TN dims, the P value
+// enters FFMA2 as a scalar-broadcast operand (no duplication); warp = NCGW chain-groups x NDGW dim-groups.
+template <int TM, int TN, int NCGW, int NDGW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) warp_generic_kernel(float* out, int steps) {
+    constexpr int K = 100, QS = NCGW * TM, PS = NDGW * TN;
+    static_assert(TM % 2 == 0 && NCGW * NDGW <= 32, "tile");
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;                                   // K * PS
+    float* Q = sm + K * PS + (threadIdx.x >> 5) * (K * QS);
+    for (int t = threadIdx.x; t < K * PS; t += blockDim.x) P[t] = 1e-3f * ((t * 7) % 13 - 6);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < K * QS; t += 32) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncthreads();
+    const bool active = lane < NCGW * NDGW;
+    const int cg = active ? lane / NDGW : 0, dg = active ? lane % NDGW : 0;
+    float2 acc[TM / 2][TN];
+#pragma unroll
+    for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[c][j] = make_float2(0.f, 0.f);
+    const float* qp = Q + cg * TM;
+    const float* pp = P + dg * TN;
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            float qv[TM], pv[TN];
+            if constexpr (TM % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < TM / 4; ++i) *reinterpret_cast<float4*>(&qv[4 * i]) = *reinterpret_cast<const float4*>(qp + k * QS + 4 * i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM / 2; ++i) *reinterpret_cast<float2*>(&qv[2 * i]) = *reinterpret_cast<const float2*>(qp + k * QS + 2 * i);
+            }
+            if constexpr (TN % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < TN / 4; ++i) *reinterpret_cast<float4*>(&pv[4 * i]) = *reinterpret_cast<const float4*>(pp + k * PS + 4 * i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < TN / 2; ++i) *reinterpret_cast<float2*>(&pv[2 * i]) = *reinterpret_cast<const float2*>(pp + k * PS + 2 * i);
+            }
+#pragma unroll
+            for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) ffma2(acc[c][j], make_float2(qv[2 * c], qv[2 * c + 1]), make_float2(pv[j], pv[j]));
+        }
+        if (acc[0][0].x == 123.456f) Q[lane] = acc[0][1].y;
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) r += acc[c][j].x + acc[c][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 template <typename F>
 double time_ms(F launch, int reps = 3) {
     cudaEvent_t e0, e1;
@@ -256,6 +349,51 @@ int main() {
         const double flop = 2.0 * 100 * 96 * 160.0 * sms * steps;
         double ms = time_ms([&] { k1<<<sms, W * 32, smem>>>(out, steps); });
         printf("(C) CTA tile 8x4 Pdup FFMA2, %d warps: %.2f TFLOP/s useful\n", W, flop / (ms * 1e-3) / 1e12);
+    }
+
+    {
+        static float hP[100 * 100];
+        for (int i = 0; i < 100 * 100; ++i) hP[i] = 1e-3f * ((i * 7) % 13 - 6);
+        CK(cudaMemcpyToSymbol(Pc, hP, sizeof(hP)));
+        const double flop_per_warp = 2.0 * 100 * 100 * 64.0 * steps;
+#define RUN_D(TN, W, CTAS)                                                                                   \
+        {                                                                                                    \
+            const size_t smem = sizeof(float) * W * 100 * 66;                                                \
+            auto kd = lane_chain_kernel<TN, W>;                                                              \
+            CK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            double ms = time_ms([&] { kd<<<sms * CTAS, W * 32, smem>>>(out, steps); });                      \
+            printf("(D) lane-owns-2-chains, slice %d dims, %d warps x %d CTA/SM: %.2f TFLOP/s useful\n", TN, W, CTAS, \
+                   flop_per_warp * W * CTAS * sms / (ms * 1e-3) / 1e12);                                     \
+        }
+        RUN_D(25, 4, 1)
+        RUN_D(20, 4, 1)
+        RUN_D(50, 4, 1)
+        RUN_D(25, 1, 4)
+        RUN_D(25, 2, 2)
+        RUN_D(25, 8, 1)
+        RUN_D(10, 8, 1)
+    }
+
+    {
+#define RUN_E(TM, TN, NCGW, NDGW, W)                                                                          \
+        {                                                                                                    \
+            const size_t smem = sizeof(float) * (100 * NDGW * TN + W * 100 * NCGW * TM);                     \
+            auto ke = warp_generic_kernel<TM, TN, NCGW, NDGW, W>;                                            \
+            CK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            double ms = time_ms([&] { ke<<<sms, W * 32, smem>>>(out, steps); });                             \
+            printf("(E) TM=%d TN=%d warp %dx%d, %d warps (smem %zu KB): %.2f TFLOP/s useful\n", TM, TN, NCGW, NDGW, W, smem / 1024, \
+                   2.0 * 100 * (NDGW * TN) * (double)(NCGW * TM) * W * sms * steps / (ms * 1e-3) / 1e12);   \
+        }
+        RUN_E(8, 10, 3, 10, 8)
+        RUN_E(8, 10, 3, 10, 12)
+        RUN_E(6, 10, 3, 10, 12)
+        RUN_E(4, 20, 6, 5, 12)
+        RUN_E(4, 10, 3, 10, 16)
+        RUN_E(8, 4, 4, 8, 16)
+        RUN_E(8, 8, 4, 8, 8)
+        RUN_E(8, 8, 4, 8, 12)
+        RUN_E(8, 12, 4, 8, 8)
+        RUN_E(4, 25, 8, 4, 8)
     }
     CK(cudaFree(out));
     return 0;
