@@ -6,7 +6,7 @@ accept/reject decisions on the reference's draws"):
     largest |q|), energies within 1e-9 relative, identical acceptance counts and chain-0 decisions;
   * float32 kernels, teacher forced (every iteration restarted from the oracle's q_initial): trajectory end
     points within rel-L2 1e-5 for L < 20 (SURVEY H4 measured 2e-7..6e-6), decisions identical except
-    near ties |ln u + dE| < 1e-3 * max(1, |E|) which are counted and bounded.
+    near ties |ln u + dE| < 1e-5 * max(1, |E|) (float32 energy resolution), which are counted and bounded.
 """
 import numpy as np
 import pytest
@@ -67,40 +67,52 @@ def _teacher_forced(fx, dtype, kernel, always_accept):
     return R, H, B
 
 
+FAST_OK = ("random_case3c_small", "random_case2c_small")     # the FFMA2 kernel covers 40 < D <= 100
+
+
 @pytest.mark.parametrize("kernel", ["generic", "fast"])
 @pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small", "random_case2c_small"])
 def test_f32_teacher_forced_trajectories(name, kernel):
+    if kernel == "fast" and name not in FAST_OK:
+        pytest.skip("fast kernel covers 40 < D <= 100")
     fx = load(name)
     R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=True)
     D = int(fx["D"])
     got = H.q_chain[:, 1, :]
     want = R.q_prop.reshape(B, D)
-    rel = np.linalg.norm(got - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
+    # relative to the amplitude of the trajectory (an end point may pass arbitrarily close to the origin)
+    amp = np.maximum(np.linalg.norm(want, axis=1), np.linalg.norm(R.q_init.reshape(B, D), axis=1))
+    rel = np.linalg.norm(got - want, axis=1) / amp
     assert rel.max() < 1e-5, "worst rel-L2 trajectory error %.3g" % rel.max()
-    # E_initial is stored at index 1 (warm_up_num = 0): float32 state, float64 scalar arithmetic
+    # E_initial is stored at index 1 (warm_up_num = 0): computed from the float32-rounded start point, so its
+    # error is |grad V| * 6e-8 |q| (cond(P) ~ 1900 at rho = 0.95): a few 1e-6 relative.
     E_want = R.E_init_iter.reshape(B)
-    np.testing.assert_allclose(H.E_chain[:, 1, 0], E_want, rtol=2e-6, atol=2e-5)
+    np.testing.assert_allclose(H.E_chain[:, 1, 0], E_want, rtol=3e-5, atol=3e-5)
 
 
 @pytest.mark.parametrize("kernel", ["generic", "fast"])
 @pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small"])
 def test_f32_teacher_forced_decisions(name, kernel):
+    if kernel == "fast" and name not in FAST_OK:
+        pytest.skip("fast kernel covers 40 < D <= 100")
     fx = load(name)
     R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=False)
     D = int(fx["D"])
     want_dec = R.decision.reshape(B)
     want_q = np.where(want_dec[:, None] == 1, R.q_prop.reshape(B, D), R.q_init.reshape(B, D))
     got_q = H.q_chain[:, 1, :]
-    got_dec = np.linalg.norm(got_q - R.q_init.reshape(B, D), axis=1) > 0       # moved <=> accepted
+    qi = R.q_init.reshape(B, D)
+    got_dec = np.linalg.norm(got_q - qi, axis=1) > 1e-5 * np.linalg.norm(qi, axis=1)       # moved <=> accepted
     dE = R.dE_iter.reshape(B)
     lnu = np.log(R.u_tape.reshape(B))
     margin = np.abs(lnu + dE)
-    near_tie = (dE >= 0) & (margin < 1e-3 * np.maximum(1.0, np.abs(R.E_init_iter.reshape(B))))
+    near_tie = (dE >= 0) & (margin < 1e-5 * np.maximum(1.0, np.abs(R.E_init_iter.reshape(B))))
     differ = got_dec != (want_dec == 1)
     assert not np.any(differ & ~near_tie), "decision flips away from ties: %d" % int(np.sum(differ & ~near_tie))
     assert near_tie.mean() < 0.02
     ok = ~differ
-    rel = np.linalg.norm(got_q[ok] - want_q[ok], axis=1) / np.maximum(np.linalg.norm(want_q[ok], axis=1), 1e-30)
+    amp = np.maximum(np.linalg.norm(want_q, axis=1), np.linalg.norm(qi, axis=1))
+    rel = np.linalg.norm(got_q[ok] - want_q[ok], axis=1) / amp[ok]
     assert rel.max() < 1e-5
 
 

@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
             const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
             T w[NL];         // w[(i - lag0) % NL] = x[i - lag0]
-            float acc[NL];
+            T acc[NL];
 #pragma unroll
-            for (int k = 0; k < NL; ++k) { w[k] = T(0); acc[k] = 0.f; }
+            for (int k = 0; k < NL; ++k) { w[k] = T(0); acc[k] = T(0); }
             long i0 = lag0;
             // first block: entry k is valid only once i - lag0 - k >= 0, i.e. k <= r (compile-time)
             {
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                         w[r] = x[(i - lag0) * D];
 #pragma unroll
                         for (int k = 0; k < NL; ++k) {
-                            if (k <= r) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                            if (k <= r) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
                         }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = T(0); }
                 i0 += NL;
             }
             for (; i0 + NL <= n; i0 += NL) {        // steady state, no conditions
@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                     const T xa = x[i * D];
                     w[r] = x[(i - lag0) * D];
 #pragma unroll
-                    for (int k = 0; k < NL; ++k) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                    for (int k = 0; k < NL; ++k) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
                 }
 #pragma unroll
-                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = T(0); }
             }
             if (i0 < n) {                            // tail
 #pragma unroll
@@ -113,11 +113,11 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                         const T xa = x[i * D];
                         w[r] = x[(i - lag0) * D];
 #pragma unroll
-                        for (int k = 0; k < NL; ++k) { const float df = (float)(xa - w[(r - k + NL) % NL]); acc[k] = fmaf(df, df, acc[k]); }
+                        for (int k = 0; k < NL; ++k) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = 0.f; }
+                for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = T(0); }
             }
         }
 #pragma unroll
