@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- leapfrog gradient-evals/sec of the fused HMC trajectory kernel (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload = "case3c_65536"): Case 3c of the reference (case3-script.py:136-181): MVN D=100,
+rho=0.95, random trajectory length L in {5..19}, dt=0.1, scaled to 65,536 chains PER GPU (weak scaling:
+chains are independent units, no data-path collective).  A "step" is one launch of the fused
+kernel over one ITERATION BLOCK (50 HMC iterations of every chain, ~12 leapfrog steps each, every iteration
+stored: thin=1, warm-up 0).  Definitions printed with the number:
+  gradient-eval = one full grad U = P (q - mu) for one chain = 2 D^2 = 20,000 flop; value counts the
+  leapfrog gradient evaluations sum(L) only (the extra evaluation after a rejected proposal and at chain
+  start is NOT counted, but is included in roofline.achieved since the kernel does execute it).
+
+value      : device-timed (CUDA events on the launching stream, barrier + synchronize on both sides, max over
+             ranks), chain state resident in HBM.
+e2e        : the same metric through the public API (samplers.HMC_sampler.gen_sample + compute_convergence_stats)
+             with q_start in pinned HOST memory (H2D inside the timed region) and the diagnostics' result read
+             back to the host (D2H inside); at N>1 the Rhat/ESS moments go through the NCCL all-reduce.
+roofline   : FP32 FMA bound (not HBM, not tensor): achieved = executed gradient evals * 2 D^2 / kernel time;
+             peak = FFMA microbenchmark measured in this run on this GPU (MEASURED_PEAKS.json has no FP32 figure).
+cpu_baseline / --impl reference : the oracle port of the reference sampler (oracle/hmc_oracle.py) with the
+             reference's own library calls (scipy logpdf for V, np.random.multivariate_normal for p), one
+             process per host core, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "understanding-hmc_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+if "reference" in sys.argv:
+    # the CPU arm runs one single-threaded process per core: BLAS/OpenMP pools must be pinned to 1 thread
+    # BEFORE numpy/scipy load (the reference's 100x100 factorizations are 7.6x slower when oversubscribed)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = "1"
+
+import numpy as np  # noqa: E402
+
+D, RHO, DT, L_LOW, L_HIGH = 100, 0.95, 0.1, 5, 20
+CHAINS_PER_GPU = 65536
+ITER_BLOCK = 50
+METRIC = "leapfrog grad-evals/sec, D=100 rho=0.95 MVN (Case 3c), 65536 chains per B200"
+UNIT = "grad-evals/s"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port), also used for cpu_baseline
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, nchain, niter = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import hmc_oracle as O
+    from scipy.stats import multivariate_normal
+    q0 = np.zeros(D)
+    cov0 = O.equicorrelated_cov(D, RHO)
+    inv_cov0 = np.linalg.inv(cov0)
+
+    def V(q):                                   # case3-script.py:39-43 -> utils.py:213-218 (scipy logpdf)
+        return -multivariate_normal.logpdf(q, mean=q0, cov=cov0)
+
+    def dVdq(q):                                # case3-script.py:45-49
+        return np.dot(inv_cov0, (q - q0))
+
+    np.random.seed(seed)
+    q_start = np.random.multivariate_normal(q0, np.diag(np.ones(D)) * 2, size=nchain)
+    t0 = time.time()
+    R = O.gen_sample_random(D, V, dVdq, q_start, O.NumpyDraws(D), nchain, niter, 1, 0, DT, L_LOW, L_HIGH, record=True)
+    dt = time.time() - t0
+    return int(R.L_tape.sum()), dt
+
+
+def cpu_reference(nchain_per_proc=8, niter=60, cores=None):
+    """Returns (leapfrog grad-evals/s over all processes, cores, description).  Counts one gradient-eval per
+    leapfrog step, like `value` (the reference itself spends two dVdq calls per step, samplers.py:835-837)."""
+    import multiprocessing as mp
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cores = cores or max(1, min(avail, 64))
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_cpu_worker, [(1000 + i, nchain_per_proc, niter) for i in range(cores)])
+    wall = time.time() - t0
+    total_L = sum(o[0] for o in out)
+    busy = max(o[1] for o in out)
+    sample = "%d procs x %d chains x %d iterations of Case 3c (D=100, rho=0.95), OMP_NUM_THREADS=1" % (cores, nchain_per_proc, niter)
+    return total_L / busy, cores, sample, wall
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.rows = []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--iter-block", type=int, default=ITER_BLOCK)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    T0 = time.time()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 0)
+    K = max(args.steps, 1)
+    config = {"workload": "case3c_65536", "D": D, "rho": RHO, "dt": DT, "L": "[%d,%d)" % (L_LOW, L_HIGH),
+              "chains_per_gpu": args.chains, "iter_block": args.iter_block, "sampler": "Random",
+              "parallelism": "chains sharded, %d rank(s)" % world,
+              "l2": "state is on-chip; each step streams a fresh %.2f GB output slab per GPU (> 126 MB L2)" %
+                    (args.chains * args.iter_block * (D * 4 + 16) / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        cores = sample = None
+        for i in range(W + K):
+            v, cores, sample, _ = cpu_reference()
+            if i >= W:
+                vals.append(v)
+        value = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hmc_b200_lib as L
+    import samplers as S
+    from oracle import hmc_oracle as O   # target construction only (cov/precision); nothing timed calls it
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    def log(msg):
+        if rank == 0:
+            sys.stderr.write("[bench %.1fs] %s\n" % (time.time() - T0, msg))
+            sys.stderr.flush()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cov0 = O.equicorrelated_cov(D, RHO)
+    spec = S.MVNSpec.from_cov(np.zeros(D), cov0)
+    Nc = args.chains
+    id0 = rank * Nc
+    rng = np.random.RandomState(1234 + rank)
+    q_start = (rng.standard_normal((Nc, D)) * np.sqrt(2.0)).astype(np.float32)      # case3-script.py:57-58
+
+    # ---- device-resident leg: one sampler, iteration blocks of ITER_BLOCK, one launch per step ----------------
+    IB = args.iter_block
+    Niter = (W + K) * IB
+    H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random",
+                      dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="fast", seed=2026, chain_id0=id0,
+                      target=spec)
+    run = H.prepare_random(q_start)               # allocates outputs/state, builds the C-ABI argument block
+    counters = run["counters"]
+    stream = L.current_stream_ptr()
+    log("buffers ready (%d chains, %d iterations)" % (Nc, Niter))
+    for i in range(W):
+        run["args"].iter_begin, run["args"].iter_end = i * IB, (i + 1) * IB
+        L.check(lib.hmc_random_run(run["args"], stream))
+    barrier()
+    log("warm-up done")
+    c0 = counters.clone()
+    sampler_thread = ClockSampler(local_rank) if rank == 0 else None
+    if sampler_thread:
+        sampler_thread.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        run["args"].iter_begin, run["args"].iter_end = i * IB, (i + 1) * IB
+        L.check(lib.hmc_random_run(run["args"], stream))
+    ev1.record()
+    barrier()
+    if sampler_thread:
+        sampler_thread.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    log("timed region done: %.1f ms for %d steps" % (ms, K))
+    dc = (counters - c0).cpu().numpy().astype(np.int64)
+    acc_post, sumL = int(dc[1]), int(dc[2])
+    n_traj = Nc * K * IB
+    n_rej = n_traj - acc_post - int(dc[0])
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(sumL), float(sumL + n_rej)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms_max = float(t.item())
+    value = float(tot[0].item()) / (ms_max * 1e-3)
+    executed_local = float(sumL + n_rej)
+
+    # ---- FP32 roofline of the fused kernel (rank 0's kernel, its own events) -----------------------------------
+    peak = L.C.c_double(0.0)
+    L.check(lib.hmc_ffma_peak(L.C.byref(peak), 0, stream))
+    flop = executed_local * 2.0 * D * D
+    achieved = flop / (ms * 1e-3) / 1e12
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    roofline = {"bound": "fp32_ffma", "kernel": "hmc_random_fast_kernel<10,10,3,8>", "achieved": achieved,
+                "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak.value / 1e12),
+                "peak_source": "FFMA microbenchmark (hmc_ffma_peak) measured in this run; nominal 2*128*%d SMs*1.965 GHz = %.1f"
+                               % (sms, 2 * 128 * sms * 1.965e9 / 1e12),
+                "traffic": None, "launch_ms": ms / K,
+                "note": "algorithmic flop = executed gradient evals (sum L + one per rejected proposal) * 2*D^2"}
+
+    # ---- end-to-end leg through the public API, host buffers ----------------------------------------------------
+    q_pinned = torch.from_numpy(q_start).pin_memory()
+    del H, run
+    torch.cuda.empty_cache()
+    e2e_ms = []
+    e2e_L = []
+    ess = None
+    for i in range(2 + K):
+        H2 = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB, thin_rate=1, warm_up_num=0, sampler_type="Random",
+                           dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="fast", seed=77 + i,
+                           chain_id0=id0, target=spec, distributed=(world > 1))
+        barrier()
+        t0 = time.perf_counter()
+        H2.gen_sample(q_pinned, verbose=False, quiet=True)       # H2D of q_start inside
+        H2.compute_convergence_stats()                           # GPU reductions (+ NCCL all-reduce), D2H of R/n_eff
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+        ll = torch.tensor([float(H2.sum_L_local)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ll)
+        if i >= 2:
+            e2e_ms.append(float(tt.item()) * 1e3)
+            e2e_L.append(float(ll.item()))
+            ess = {"n_eff_median": float(np.median(H2.n_eff_q)), "n_eff_min": float(np.min(H2.n_eff_q)),
+                   "rhat_median": float(np.median(H2.R_q)), "stored_samples": int(world * Nc * IB),
+                   "ess_per_sec_median": float(np.median(H2.n_eff_q)) / float(tt.item()), "accept_R": H2.accept_R}
+        del H2
+    log("e2e done")
+    e2e_value = float(np.sum(e2e_L) / (np.sum(e2e_ms) * 1e-3))
+    h2d = Nc * D * 4
+    d2h = 2 * D * 8 + 3 * D * 8 + 32 * D * 8 + 4 * 8
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        # separate process: forking a pool out of a CUDA/NCCL-initialised parent is not safe
+        try:
+            out = subprocess.check_output([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                           "--warmup", "0"], timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+            cpu = json.loads(out.decode().strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:   # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (exc,)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "clocks": sampler_thread.summary() if sampler_thread else None,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": float(np.mean(e2e_ms))},
+                "gpu_launches": K,
+                "roofline": roofline, "cpu_baseline": cpu, "ess": ess,
+                "grad_evals_executed_per_sec": float(tot[1].item()) / (ms_max * 1e-3),
+                "reference_unit_steps_per_sec": value * D,
+                "accept_rate": (acc_post + int(dc[0])) / float(n_traj)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -83,7 +83,7 @@ typedef struct hmc_random_args {
     int32_t dtype;          /* HMC_F32 | HMC_F64 */
     int32_t kernel;         /* HMC_KERNEL_* */
     int32_t Nchain;         /* chains on this device */
-    int32_t reserved0;
+    int32_t flags;          /* bit 0: every entry of target.dt is equal (lets the fused kernel fold dt into constants) */
     int64_t chain_id0;      /* global id of local chain 0 */
     int32_t Niter;          /* total iterations of the run (samplers.py:26) */
     int32_t iter_begin;     /* iterations already done */

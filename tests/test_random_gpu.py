@@ -218,3 +218,28 @@ def test_target_extraction_and_errors():
     with pytest.raises(L.HMCError) as ei:
         bad.gen_sample(np.zeros((3, D)), verbose=False)
     assert ei.value.code == L.HMC_E_BADARG
+
+
+def test_fast_kernel_slot_refill_matches_generic():
+    """More chains than resident slots (148 SMs x 192): finished slots pull new chains from the queue, over
+    several iteration-block launches.  Same Philox draws as the generic kernel => same streams up to float32
+    summation order (first trajectory rel 1e-5, acceptance within 0.2 %)."""
+    import samplers as S
+    D, Nchain, Niter = 100, 40000, 4
+    spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+    q_start = np.random.RandomState(5).standard_normal((Nchain, D)).astype(np.float32) * 1.4
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=0.1, L_low=5,
+              L_high=20, dtype="float32", seed=11, target=spec)
+    F = S.HMC_sampler(D, None, None, kernel="fast", iter_block=3, **kw)
+    F.gen_sample(q_start, verbose=False, quiet=True)
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L
+    qf, qg = F.q_chain, G.q_chain
+    np.testing.assert_array_equal(qf[:, 0], qg[:, 0])
+    amp = np.linalg.norm(q_start.astype(float), axis=1)
+    rel = np.linalg.norm(qf[:, 1] - qg[:, 1], axis=1) / amp
+    assert np.quantile(rel, 0.999) < 1e-5
+    assert abs(F.accept_R - G.accept_R) < 2e-3
+    assert np.all(np.isfinite(qf)) and np.abs(qf[:, -1]).max() < 50
+    np.testing.assert_allclose(F.E_chain[:, :2, 0], G.E_chain[:, :2, 0], rtol=1e-5)

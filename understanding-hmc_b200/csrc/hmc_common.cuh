@@ -49,14 +49,15 @@ enum { HMC_STREAM_MOMENTUM = 0, HMC_STREAM_SCALAR = 1, HMC_STREAM_NUTS = 2 };
 __device__ __forceinline__ float4 hmc_normal4(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t slot) {
     Philox4 r = philox4x32_10((uint32_t)chain, iter, slot, HMC_STREAM_MOMENTUM | ((uint32_t)(chain >> 32) << 8),
                               (uint32_t)seed, (uint32_t)(seed >> 32));
-    const float S = 2.3283064365386963e-10f;  // 2^-32
-    float u1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (0,1), 24 bits
-    float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f;
-    float r1 = sqrtf(-2.0f * logf(u1));
-    float r2 = sqrtf(-2.0f * logf(u2));
-    float s1, c1, s2, c2;
-    sincospif(2.0f * ((float)r.y * S), &s1, &c1);
-    sincospif(2.0f * ((float)r.w * S), &s2, &c2);
+    // Box-Muller on the SFU (MUFU.LG2 / MUFU.SIN / MUFU.COS, abs. error ~2^-21): the refresh is on the hot path
+    // of the fused kernel; every kernel and hmc_philox_draws share this function, so all see identical draws.
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (0,1), 24 bits
+    const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float r1 = sqrtf(-2.0f * __logf(u1));
+    const float r2 = sqrtf(-2.0f * __logf(u2));
+    const float a1 = ((float)(r.y >> 8) * 5.9604644775390625e-08f - 0.5f) * 6.283185307179586f;   // [-pi, pi)
+    const float a2 = ((float)(r.w >> 8) * 5.9604644775390625e-08f - 0.5f) * 6.283185307179586f;
+    const float s1 = __sinf(a1), c1 = __cosf(a1), s2 = __sinf(a2), c2 = __cosf(a2);
     return make_float4(r1 * c1, r1 * s1, r2 * c2, r2 * s2);
 }
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void hmc_scalar_draws(uint64_t seed, uint64_t chain, 
     Philox4 r = philox4x32_10((uint32_t)chain, iter, 0u, HMC_STREAM_SCALAR | ((uint32_t)(chain >> 32) << 8),
                               (uint32_t)seed, (uint32_t)(seed >> 32));
     *L = L_low + (int)__umulhi(r.x, (uint32_t)(L_high - L_low));
-    *u = ((double)r.y + 0.5) * 2.3283064365386963e-10;
+    *u = ((double)(r.y >> 8) + 0.5) * 5.9604644775390625e-08;   // 24-bit uniform in (0,1): exact in float and double
 }
 
 // NUTS per-chain stream: draw number n of iteration iter -> (coin, uniform).

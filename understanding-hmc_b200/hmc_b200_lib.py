@@ -27,7 +27,7 @@ class Target(C.Structure):
 
 
 class RandomArgs(C.Structure):
-    _fields_ = [("dtype", C.c_int32), ("kernel", C.c_int32), ("Nchain", C.c_int32), ("reserved0", C.c_int32),
+    _fields_ = [("dtype", C.c_int32), ("kernel", C.c_int32), ("Nchain", C.c_int32), ("flags", C.c_int32),
                 ("chain_id0", C.c_int64), ("Niter", C.c_int32), ("iter_begin", C.c_int32), ("iter_end", C.c_int32),
                 ("warm_up_num", C.c_int32), ("thin_rate", C.c_int32), ("L_low", C.c_int32), ("L_high", C.c_int32),
                 ("N_save_chain0", C.c_int32), ("seed", C.c_uint64), ("target", Target), ("q_start", C.c_void_p),

@@ -252,23 +252,28 @@ class HMC_sampler(sampler):
                 dist.all_reduce(t)
         return t
 
-    def gen_sample(self, q_start, N_save_chain0=0, verbose=True):
+    def gen_sample(self, q_start, N_save_chain0=0, verbose=True, quiet=False):
         """Dispatch on sampler type (samplers.py:363-383).  "Fixed" runs the random-length loop with a constant
         L; "Static" stays the no-op it is in the reference (Q11)."""
         if (self.sampler_type == "Random"):
-            self.gen_sample_random(q_start, N_save_chain0, verbose)
+            self.gen_sample_random(q_start, N_save_chain0, verbose, quiet)
         elif (self.sampler_type == "NUTS"):
             self.gen_sample_NUTS(q_start, N_save_chain0, verbose)
         elif (self.sampler_type == "Fixed"):
             self.L_low, self.L_high = int(self.L), int(self.L) + 1
-            self.gen_sample_random(q_start, N_save_chain0, verbose)
+            self.gen_sample_random(q_start, N_save_chain0, verbose, quiet)
         return
 
-    def gen_sample_random(self, q_start, N_save_chain0, verbose):
-        """Random trajectory length sampler (samplers.py:387-491) on the GPU."""
+    def _to_device(self, torch, q_start, dev, tdt):
+        """q_start: numpy array or (pinned) host torch tensor, shape (Nchain, D)."""
+        if isinstance(q_start, torch.Tensor):
+            return q_start.to(device=dev, dtype=tdt, non_blocking=True).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(q_start), dtype=float)).to(device=dev, dtype=tdt).contiguous()
+
+    def prepare_random(self, q_start, N_save_chain0=0):
+        """Allocate the device-resident outputs/state and build the C-ABI argument block (hmc_random_args) of
+        the random-trajectory sampler; the caller launches iteration blocks with hmc_random_run."""
         import torch
-        lib = _L.load()
-        q_start = np.asarray(q_start)
         assert q_start.shape[0] == self.Nchain                                       # samplers.py:396
         dev = torch.device("cuda", torch.cuda.current_device())
         tgt, keep, tdt = self._build_target(torch, dev)
@@ -280,10 +285,10 @@ class HMC_sampler(sampler):
         self._E_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._dE_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._q_host = self._E_host = self._dE_host = None
-        qs = torch.from_numpy(np.ascontiguousarray(q_start, dtype=float)).to(device=dev, dtype=tdt).contiguous()
-        state_q = torch.empty((Nc, D), dtype=tdt, device=dev)
-        state_g = torch.empty((Nc, D), dtype=tdt, device=dev)
-        state_e = torch.zeros((Nc,), dtype=f64, device=dev)
+        keep["qs"] = self._to_device(torch, q_start, dev, tdt)
+        keep["state_q"] = torch.empty((Nc, D), dtype=tdt, device=dev)
+        keep["state_g"] = torch.zeros((max(Nc * D, 64),), dtype=tdt, device=dev)
+        keep["state_e"] = torch.zeros((Nc,), dtype=f64, device=dev)
         counters = torch.zeros((4,), dtype=torch.int64, device=dev)
         a = _L.RandomArgs()
         a.dtype = _L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64
@@ -294,7 +299,8 @@ class HMC_sampler(sampler):
         a.N_save_chain0 = int(N_save_chain0) if owns0 else 0
         a.seed = self.seed
         a.target = tgt
-        a.q_start = qs.data_ptr()
+        a.flags = 1 if np.ndim(self.dt) == 0 or np.all(np.asarray(self.dt) == np.asarray(self.dt).flat[0]) else 0
+        a.q_start = keep["qs"].data_ptr()
         if self.draws is not None:
             keep["p_tape"] = torch.from_numpy(np.ascontiguousarray(self.draws["p_tape"], dtype=float)).to(dev)
             keep["L_tape"] = torch.from_numpy(np.ascontiguousarray(self.draws["L_tape"], dtype=np.int32)).to(dev)
@@ -303,18 +309,31 @@ class HMC_sampler(sampler):
             assert keep["L_tape"].shape == (Nc, self.Niter) and keep["u_tape"].shape == (Nc, self.Niter)
             a.p_tape, a.L_tape, a.u_tape = (keep[k].data_ptr() for k in ("p_tape", "L_tape", "u_tape"))
         a.q_chain, a.E_chain, a.dE_chain = self._q_dev.data_ptr(), self._E_dev.data_ptr(), self._dE_dev.data_ptr()
-        a.state_q, a.state_g, a.state_eprev = state_q.data_ptr(), state_g.data_ptr(), state_e.data_ptr()
+        a.state_q, a.state_g, a.state_eprev = keep["state_q"].data_ptr(), keep["state_g"].data_ptr(), \
+            keep["state_e"].data_ptr()
         a.counters = counters.data_ptr()
         if save_chain and owns0:
             keep["phi"] = torch.zeros((N_save_chain0, int(self.L_high), 2), dtype=f64, device=dev)
             keep["phi_len"] = torch.zeros((N_save_chain0,), dtype=torch.int32, device=dev)
             keep["dec"] = torch.zeros((N_save_chain0 + 1,), dtype=torch.int32, device=dev)
             a.phi_q, a.phi_len, a.decision_chain = (keep[k].data_ptr() for k in ("phi", "phi_len", "dec"))
+        return dict(args=a, keep=keep, counters=counters, device=dev)
+
+    def gen_sample_random(self, q_start, N_save_chain0, verbose, quiet=False):
+        """Random trajectory length sampler (samplers.py:387-491) on the GPU."""
+        import torch
+        lib = _L.load()
+        say = (lambda *x: None) if quiet else print
+        run = self.prepare_random(q_start, N_save_chain0)
+        a, keep, counters, dev = run["args"], run["keep"], run["counters"], run["device"]
+        Nc, D = self.Nchain, self.D
+        owns0 = self.chain_id0 == 0
+        save_chain = N_save_chain0 > 0
         stream = _L.current_stream_ptr()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if verbose:
-            print("Running %d chains x %d iterations on %s (%s, kernel=%s)" %
-                  (Nc, self.Niter, torch.cuda.get_device_name(dev), self.dtype, self.kernel))
+            say("Running %d chains x %d iterations on %s (%s, kernel=%s)" %
+                (Nc, self.Niter, torch.cuda.get_device_name(dev), self.dtype, self.kernel))
         ev0.record()
         for (b, e) in self._blocks():
             a.iter_begin, a.iter_end = b, e
@@ -324,26 +343,26 @@ class HMC_sampler(sampler):
         self.kernel_ms = ev0.elapsed_time(ev1)
         if verbose:                                                                  # samplers.py:478-481 (Q10)
             self.dt_total += self.kernel_ms * 1e-3
-            print("Time taken: %.2f\n" % (self.kernel_ms * 1e-3))
+            say("Time taken: %.2f\n" % (self.kernel_ms * 1e-3))
+        self.sum_L_local = int(counters[2].item())
         c = self._all_reduce(torch, counters.clone()).cpu().numpy()
         nchain_all = self._all_reduce(torch, torch.tensor([Nc], dtype=torch.int64, device=dev)).item()
         acc_warm, acc_post, sumL, sumL2 = (int(v) for v in c)
         self.sum_L = sumL
         self.N_total_steps = nchain_all * (1 + 2 * self.Niter) + D * sumL2          # samplers.py:417,435,450,456 (Q3)
-        print("Compute acceptance rate")
+        say("Compute acceptance rate")
         if self.warm_up_num > 0:                                                     # samplers.py:484-488
             self.accept_R_warm_up = acc_warm / float(nchain_all * self.warm_up_num)
-            print("During warm up: %.3f" % self.accept_R_warm_up)
+            say("During warm up: %.3f" % self.accept_R_warm_up)
         self.accept_R = acc_post / float(nchain_all * (self.Niter - self.warm_up_num + 1))
-        print("After warm up: %.3f" % self.accept_R)
-        print("Completed.")
+        say("After warm up: %.3f" % self.accept_R)
+        say("Completed.")
         if save_chain and owns0:                                                     # samplers.py:397-400, 442-475
             nrec = min(N_save_chain0, self.Niter)
             lens = keep["phi_len"].cpu().numpy()
             phi = keep["phi"].cpu().numpy()
             self.phi_q = [phi[i, :lens[i], :].copy() for i in range(nrec)]
             self.decision_chain = keep["dec"].cpu().numpy().astype(int)[:, None]
-        self._keep = None
         return
 
     def gen_sample_NUTS(self, q_start, N_save_chain0, verbose):
