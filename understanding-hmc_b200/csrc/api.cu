@@ -127,31 +127,31 @@ extern "C" int hmc_philox_draws(uint64_t seed, int64_t chain_id0, int32_t Nchain
 // hmc_ffma_peak: FP32 FMA roofline probe
 // ---------------------------------------------------------------------------------------------------------
 template <bool kPacked>
-__global__ void __launch_bounds__(512) ffma_peak_kernel(float* out, int iters, float a0, float b0) {
-    // 16 independent accumulator pairs per thread: enough ILP to cover the 4-cycle FMA latency.
-    float2 acc[16];
+__global__ void __launch_bounds__(512) ffma_peak_kernel(float* out, int iters) {
+    // 32 independent FMA chains per thread, multiplier and addend as compile-time constants: the immediate-operand
+    // FFMA form issues every cycle, which is what the 2*128*SMs*clock nominal peak assumes (a three-register FFMA
+    // stream measured 63 % of it on B200 because of register-bank reads; FFMA2 needs register pairs anyway).
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
-    float2 a = make_float2(a0, a0 * 0.999f), b = make_float2(b0, b0 * 1.001f);
+    for (int i = 0; i < 32; ++i) acc[i] = threadIdx.x * 1e-3f + i;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
             if (kPacked) {
-                unsigned long long A, B, C;
-                A = *reinterpret_cast<unsigned long long*>(&a);
-                B = *reinterpret_cast<unsigned long long*>(&acc[i]);
-                C = *reinterpret_cast<unsigned long long*>(&b);
-                asm volatile("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(B) : "l"(A), "l"(C));
-                acc[i] = *reinterpret_cast<float2*>(&B);
+                float2 v = make_float2(acc[i], acc[(i + 1) & 31]);
+                unsigned long long B = *reinterpret_cast<unsigned long long*>(&v);
+                const float2 ca = make_float2(0.999f, 0.998f), cb = make_float2(0.001f, 0.002f);
+                asm volatile("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(B) : "l"(*reinterpret_cast<const unsigned long long*>(&ca)),
+                             "l"(*reinterpret_cast<const unsigned long long*>(&cb)));
+                acc[i] = reinterpret_cast<float2*>(&B)->x;
             } else {
-                acc[i].x = fmaf(a.x, acc[i].x, b.x);
-                acc[i].y = fmaf(a.y, acc[i].y, b.y);
+                acc[i] = fmaf(0.999f, acc[i], 0.001f);
             }
         }
     }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+    for (int i = 0; i < 32; ++i) s += acc[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -170,13 +170,13 @@ extern "C" int hmc_ffma_peak(double* out_flops_host, int32_t use_ffma2, void* cu
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         HMC_CUDA_CHECK(cudaEventRecord(e0, stream));
-        if (use_ffma2) ffma_peak_kernel<true><<<blocks, threads, 0, stream>>>(buf, iters, 0.999f, 0.001f);
-        else ffma_peak_kernel<false><<<blocks, threads, 0, stream>>>(buf, iters, 0.999f, 0.001f);
+        if (use_ffma2) ffma_peak_kernel<true><<<blocks, threads, 0, stream>>>(buf, iters);
+        else ffma_peak_kernel<false><<<blocks, threads, 0, stream>>>(buf, iters);
         HMC_CUDA_CHECK(cudaEventRecord(e1, stream));
         HMC_CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0.f;
         HMC_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 32.0 * iters * (double)blocks * threads / (ms * 1e-3);
+        const double flops = 2.0 * 32.0 * (use_ffma2 ? 2.0 : 1.0) * iters * (double)blocks * threads / (ms * 1e-3);
         if (rep > 0 && flops > best) best = flops;
     }
     HMC_CUDA_CHECK(cudaGetLastError());

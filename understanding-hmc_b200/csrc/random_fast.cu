@@ -20,7 +20,6 @@
 
 namespace {
 
-constexpr int TM = 8;  // chains per lane (4 FFMA2 pairs)
 
 __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
     unsigned long long D;
@@ -34,16 +33,30 @@ __device__ __forceinline__ float2 bc2(const float x) { return make_float2(x, x);
 
 enum SlotState : int { ST_IDLE = 0, ST_RUN = 1, ST_NEED_CHAIN = 2, ST_ACC = 3, ST_REJ = 4 };
 
-template <int TN, int NDG, int NCG>
+template <int TM, int TN, int NDG, int NCG>
 struct Geo {
     static constexpr int NSLOT = NCG * TM;       // chain slots per warp
     static constexpr int DP = NDG * TN;          // padded dimension
-    static constexpr int QS = NSLOT + 4;         // row stride of the live position tile: (NSLOT+4)/4 odd => the
-                                                 // lanes of a quarter warp hit distinct banks in the update pass
-    static constexpr int Q0S = NSLOT;            // row stride of the iteration-start tile
+    // row stride of the position tile: a multiple of 4 floats with QS/4 odd, so that the lanes of a quarter warp
+    // hit distinct banks in the update pass
+    static constexpr int QS = ((NSLOT + 3) / 4) % 2 ? (NSLOT + 3) / 4 * 4 : (NSLOT + 3) / 4 * 4 + 4;
+    static constexpr int RW = 2 * TM;            // floats per lane in the reduction scratch
+    static constexpr int BK = 32 * 16;           // per-slot bookkeeping block (16 words per slot)
     static constexpr int STAGE = (DP + 31) / 32 * 32 + 32;
-    static constexpr int RED = 32 * 16;
+    static constexpr int RED = 32 * 2 * TM;
 };
+
+// Per-slot bookkeeping, kept in shared memory (one 64-byte record per slot) so that it costs no registers in
+// the gradient loop.  Only lane s touches record s, except for the warp-uniform reads in the service loop.
+struct __align__(16) SlotBk {
+    int state, m, it, l;
+    int L, init;
+    float K0, Knew;
+    double Einit, Eprev, V;
+    float lnu;
+    int pad;
+};
+static_assert(sizeof(SlotBk) == 64, "SlotBk layout");
 
 struct GenArgs {
     uint64_t seed;
@@ -102,21 +115,24 @@ __device__ __noinline__ void gen_momentum(const GenArgs a, long m, uint64_t gid,
     __syncwarp();
 }
 
-template <int TN, int NDG, int NCG, int WARPS, bool UDT>
+template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL>
 __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
-    using G = Geo<TN, NDG, NCG>;
-    constexpr int NSLOT = G::NSLOT, DP = G::DP, QS = G::QS, Q0S = G::Q0S;
+    using G = Geo<TM, TN, NDG, NCG>;
+    static_assert(TM % 4 == 0 && G::NSLOT <= 32, "tile");
+    constexpr int NSLOT = G::NSLOT, DP = G::DP, QS = G::QS;
     extern __shared__ __align__(16) float sm[];
-    const int D = a.target.D;
+    const int D = FULL ? Geo<TM, TN, NDG, NCG>::DP : a.target.D;          // FULL: the tile has no padded dimensions
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* Ps = sm;                       // [D][DP]   Ps[k][dg*TN + jj] = P[k][jj*NDG + dg]
     float* mu_s = Ps + D * DP;            // [DP]
     float* dt_s = mu_s + DP;              // [DP]
-    float* wbase = dt_s + DP + (size_t)warp * (D * QS + D * Q0S + G::RED + G::STAGE);
+    float* wbase = dt_s + DP + (size_t)warp * (D * QS + G::RED + G::STAGE + G::BK);
     float* Ds = wbase;                    // [D][QS]   live positions (shifted by mu)
-    float* D0s = Ds + D * QS;             // [D][Q0S]  positions at the start of the running iteration
-    float* red = D0s + D * Q0S;           // [32][16]  per-lane partial sums
+    float* red = Ds + D * QS;             // [32][16]  per-lane partial sums
     float* stage = red + G::RED;          // momentum staging
+    SlotBk* bk = reinterpret_cast<SlotBk*>(stage + G::STAGE);   // [32] per-slot bookkeeping
+    // The position at the start of the running iteration (what a rejection restores) lives in HBM/L2: state_q.
+    float* q0g = (float*)a.state_q;
     {
         const float* Ft = (const float*)a.target.Ft;
         const int Dpad = a.target.D_pad;
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = lane; t < D * QS + D * Q0S; t += 32) Ds[t] = 0.f;
+        for (int t = lane; t < D * QS; t += 32) Ds[t] = 0.f;
         __syncthreads();
     }
     const bool active = lane < NCG * NDG;
@@ -145,29 +161,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
 #pragma unroll
         for (int j = 0; j < TN; ++j) { g[c][j] = make_float2(0.f, 0.f); p[c][j] = make_float2(0.f, 0.f); }
 
-    // ---- per-slot bookkeeping, held by lane s < NSLOT --------------------------------------------------------
-    int bk_state = (lane < NSLOT) ? ST_NEED_CHAIN : ST_IDLE;
-    int bk_m = -1;
-    int bk_it = 0, bk_l = 0, bk_L = 1;
-    bool bk_init = false;
-    double bk_Einit = 0.0, bk_Eprev = 0.0, bk_V = 0.0;
-    float bk_K0 = 0.f, bk_Knew = 0.f, bk_lnu = 0.f;
+    // ---- per-slot bookkeeping lives in shared memory (SlotBk), record s is owned by lane s < NSLOT -------------
+    if (lane < 32) {
+        SlotBk z;
+        z.state = (lane < NSLOT) ? ST_NEED_CHAIN : ST_IDLE; z.m = -1; z.it = 0; z.l = 0; z.L = 1; z.init = 0;
+        z.K0 = 0.f; z.Knew = 0.f; z.Einit = 0.0; z.Eprev = 0.0; z.V = 0.0; z.lnu = 0.f; z.pad = 0;
+        bk[lane] = z;
+    }
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
-    const double vconst = a.target.v_const;
     GenArgs ga;
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
     ga.D = D; ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
+    __syncwarp();
 
     while (true) {
         // ===== A. service every slot that finished a trajectory or needs a chain (warp-uniform loop) ==========
-        unsigned need = __ballot_sync(HMC_FULL_MASK, bk_state >= ST_NEED_CHAIN);
+        unsigned need = __ballot_sync(HMC_FULL_MASK, bk[lane].state >= ST_NEED_CHAIN);
         while (need) {
             const int s = __ffs(need) - 1;
             need &= need - 1;
             const int scg = s / TM, sc = s % TM;
-            int kind = __shfl_sync(HMC_FULL_MASK, bk_state, s);
-            long m = __shfl_sync(HMC_FULL_MASK, bk_m, s);
-            int it = __shfl_sync(HMC_FULL_MASK, bk_it, s);
+            int kind = bk[s].state;                 // uniform (broadcast) reads
+            long m = bk[s].m;
+            int it = bk[s].it;
             const bool owner = active && (cg == scg);
             float dv[TN];
 #pragma unroll
@@ -177,25 +193,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                 //      (samplers.py:462-472)
                 const bool keep = it >= a.warm_up_num;
                 const long idx = keep ? (it - a.warm_up_num) / a.thin_rate : 0;
-                const bool last_it = it >= a.iter_end;
                 if (owner) {
                     float* dst = q_chain + ((size_t)m * Lc + idx) * D;
-                    float* fin = (float*)a.state_q + (size_t)m * D;
+                    float* q0 = q0g + (size_t)m * D;
 #pragma unroll
                     for (int jj = 0; jj < TN; ++jj) {
                         const int j = jj * NDG + dg;
-                        if (j < D) {
-                            if (kind == ST_ACC) { dv[jj] = Ds[j * QS + s]; D0s[j * Q0S + s] = dv[jj]; }
-                            else { dv[jj] = D0s[j * Q0S + s]; Ds[j * QS + s] = dv[jj]; }
-                            const float qv = dv[jj] + mu_s[j];
+                        if (FULL || j < D) {
+                            float qv;
+                            if (kind == ST_ACC) { dv[jj] = Ds[j * QS + s]; qv = dv[jj] + mu_s[j]; q0[j] = qv; }
+                            else { qv = q0[j]; dv[jj] = qv - mu_s[j]; Ds[j * QS + s] = dv[jj]; }
                             if (keep) dst[j] = qv;
-                            if (last_it) fin[j] = qv;
                         }
                     }
                 }
-                if (last_it) {
-                    if (lane == s) a.state_eprev[m] = bk_Eprev;
-                    kind = ST_NEED_CHAIN;       // chain finished: the slot asks for the next one
+                if (it >= a.iter_end) {
+                    // chain finished: state_q already holds its position; the slot asks for the next chain
+                    if (lane == s) a.state_eprev[m] = bk[s].Eprev;
+                    kind = ST_NEED_CHAIN;
                 }
             }
             if (kind == ST_NEED_CHAIN) {
@@ -206,9 +221,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     // queue empty: park the slot with finite numbers
                     if (owner) {
 #pragma unroll
-                        for (int jj = 0; jj < TN; ++jj) { const int j = jj * NDG + dg; if (j < D) { Ds[j * QS + s] = 0.f; D0s[j * Q0S + s] = 0.f; } }
+                        for (int jj = 0; jj < TN; ++jj) { const int j = jj * NDG + dg; if (FULL || j < D) Ds[j * QS + s] = 0.f; }
                     }
-                    if (lane == s) { bk_state = ST_IDLE; bk_m = -1; }
+                    if (lane == s) { bk[s].state = ST_IDLE; bk[s].m = -1; }
 #pragma unroll
                     for (int c2 = 0; c2 < TM / 2; ++c2) {
                         const bool hx = owner && (sc == 2 * c2), hy = owner && (sc == 2 * c2 + 1);
@@ -223,28 +238,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                 }
                 m = (long)nxt;
                 it = a.iter_begin;
-                const float* src = (a.iter_begin == 0) ? (const float*)a.q_start : (const float*)a.state_q;
                 if (owner) {
+                    float* q0 = q0g + (size_t)m * D;
 #pragma unroll
                     for (int jj = 0; jj < TN; ++jj) {
                         const int j = jj * NDG + dg;
-                        if (j < D) {
-                            const float qv = src[(size_t)m * D + j];
+                        if (FULL || j < D) {
+                            float qv;
+                            if (a.iter_begin == 0) {
+                                qv = ((const float*)a.q_start)[(size_t)m * D + j];
+                                q0[j] = qv;
+                                q_chain[(size_t)m * Lc * D + j] = qv;                       // samplers.py:413
+                            } else {
+                                qv = q0[j];
+                            }
                             dv[jj] = qv - mu_s[j];
                             Ds[j * QS + s] = dv[jj];
-                            D0s[j * Q0S + s] = dv[jj];
-                            if (a.iter_begin == 0) q_chain[(size_t)m * Lc * D + j] = qv;      // samplers.py:413
                         }
                     }
                 }
                 if (a.iter_begin == 0) {                                                   // samplers.py:415 (K only)
                     float k0, ld; int Ld;
                     gen_momentum(ga, m, (uint64_t)(a.chain_id0 + m), 0, lane, stage, &k0, &Ld, &ld);
-                    if (lane == s) { bk_K0 = 0.5f * k0; bk_init = true; }
+                    if (lane == s) { bk[s].K0 = 0.5f * k0; bk[s].init = 1; }
                     if (a.decision_chain && a.chain_id0 + m == 0 && lane == s) a.decision_chain[a.N_save_chain0] = 0;
                 } else if (lane == s) {
-                    bk_Eprev = a.state_eprev[m];
-                    bk_init = false;
+                    bk[s].Eprev = a.state_eprev[m];
+                    bk[s].init = 0;
                 }
             }
             // ---- start iteration it+1: momentum refresh (samplers.py:431), trajectory length (:441), uniform (:461)
@@ -255,70 +275,64 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             const bool go = (kind == ST_ACC);      // gradient at the accepted point is still in g: kick and drift now
             const bool tr = a.phi_q && gid == 0 && itn <= a.N_save_chain0;
             if (lane == s) {
-                bk_m = (int)m; bk_it = itn; bk_L = Ln; bk_lnu = lnun; bk_Knew = 0.5f * ksum; bk_state = ST_RUN;
+                SlotBk b = bk[s];
+                b.m = (int)m; b.it = itn; b.L = Ln; b.lnu = lnun; b.Knew = 0.5f * ksum; b.state = ST_RUN;
                 n_sumL += (unsigned int)Ln; n_sumL2 += (unsigned int)(Ln * Ln);
                 if (go) {
                     // E_initial of the new iteration (samplers.py:434-438): V at the accepted point + new kinetic energy
-                    bk_Einit = bk_V + (double)bk_Knew;
+                    b.Einit = b.V + (double)b.Knew;
                     if (itn >= a.warm_up_num) {
                         const long idx = (itn - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)m * Lc + idx] = bk_Einit;
-                        a.dE_chain[(size_t)m * Lc + idx] = bk_Einit - bk_Eprev;
+                        a.E_chain[(size_t)m * Lc + idx] = b.Einit;
+                        a.dE_chain[(size_t)m * Lc + idx] = b.Einit - b.Eprev;
                     }
-                    bk_l = 1;
+                    b.l = 1;
                 } else {
-                    bk_l = 0;
+                    b.l = 0;
                 }
-                if (tr) {
-                    double* phi = a.phi_q + (size_t)(itn - 1) * a.L_high * 2;
-                    phi[0] = (double)(D0s[s] + mu_s[0]);
-                    if (D > 1) phi[1] = (double)(D0s[Q0S + s] + mu_s[1]);
-                    a.phi_len[itn - 1] = Ln + 1;
-                }
+                bk[s] = b;
             }
             // ---- owners: new momentum (+ first half kick and drift when the gradient is at hand) -----------------
-            float pn[TN];
-            if (owner) {
+            {
                 const bool odd = sc & 1;
                 const int sp = sc >> 1;
 #pragma unroll
                 for (int jj = 0; jj < TN; ++jj) {
                     const int j = jj * NDG + dg;
-                    float pj = (j < D) ? stage[j] : 0.f;
+                    float pj = (FULL || j < D) ? stage[j] : 0.f;
                     if (go) {
-                        const float2 g01 = (sp == 0) ? g[0][jj] : (sp == 1) ? g[1][jj] : (sp == 2) ? g[2][jj] : g[3][jj];
+                        float2 g01 = g[0][jj];
+#pragma unroll
+                        for (int c2 = 1; c2 < TM / 2; ++c2) if (sp == c2) g01 = g[c2][jj];
                         const float gj = odd ? g01.y : g01.x;
                         const float dtj = UDT ? dt0 : dt_s[j];
-                        pj = fmaf(gj, -0.5f * dtj, pj);                    // first half kick (samplers.py:835)
-                        if (j < D) Ds[j * QS + s] = fmaf(pj, dtj, dv[jj]);     // drift (samplers.py:836)
+                        pj = fmaf(gj, -0.5f * dtj, pj);                                        // first half kick (samplers.py:835)
+                        if (owner && (FULL || j < D)) Ds[j * QS + s] = fmaf(pj, dtj, dv[jj]);   // drift (samplers.py:836)
                     }
-                    pn[jj] = pj;
-                }
-            }
 #pragma unroll
-            for (int c2 = 0; c2 < TM / 2; ++c2) {
-                const bool hx = owner && (sc == 2 * c2), hy = owner && (sc == 2 * c2 + 1);
-#pragma unroll
-                for (int jj = 0; jj < TN; ++jj) {
-                    if (hx) p[c2][jj].x = pn[jj];
-                    if (hy) p[c2][jj].y = pn[jj];
+                    for (int c2 = 0; c2 < TM / 2; ++c2) {
+                        if (owner && sc == 2 * c2) p[c2][jj].x = pj;
+                        if (owner && sc == 2 * c2 + 1) p[c2][jj].y = pj;
+                    }
                 }
             }
             __syncwarp();
-            if (tr && go && lane == s) {
+            if (tr && lane == s) {
+                // chain-0 trajectory capture (samplers.py:442-452): row 0 is the start point, row 1 the first step
                 double* phi = a.phi_q + (size_t)(itn - 1) * a.L_high * 2;
-                phi[2] = (double)(Ds[s] + mu_s[0]);
-                if (D > 1) phi[3] = (double)(Ds[QS + s] + mu_s[1]);
+                const float* q0 = q0g + (size_t)m * D;
+                phi[0] = (double)q0[0];
+                if (D > 1) phi[1] = (double)q0[1];
+                a.phi_len[itn - 1] = Ln + 1;
+                if (go) {
+                    phi[2] = (double)(Ds[s] + mu_s[0]);
+                    if (D > 1) phi[3] = (double)(Ds[QS + s] + mu_s[1]);
+                }
             }
         }
 
         // ===== B. done when no slot runs ====================================================================
-        const unsigned run = __ballot_sync(HMC_FULL_MASK, bk_state == ST_RUN);
-        if (run == 0u) break;
-        // point index of the gradient about to be evaluated: 0 = first point, L = last point of the trajectory
-        const unsigned m_l0 = __ballot_sync(HMC_FULL_MASK, bk_state == ST_RUN && bk_l == 0);
-        const unsigned m_last = __ballot_sync(HMC_FULL_MASK, bk_state == ST_RUN && bk_l == bk_L);
-        const unsigned m_mid = run & ~m_l0 & ~m_last;
+        if (__ballot_sync(HMC_FULL_MASK, bk[lane].state == ST_RUN) == 0u) break;
 
         // ===== C. gradient  g[c][j] = sum_k d[k][c] P[k][j]  ==================================================
 #pragma unroll
@@ -349,25 +363,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
         __syncwarp();
 
         // ===== D. leapfrog update of the lane's tile (samplers.py:835-837) + energy partial sums ================
-        // per chain: interior points take the second half kick of step l and the first half kick of step l+1
-        // (kick weight -1), the first and last point of a trajectory one half kick (-1/2); the position moves
-        // at every point but the last.
+        // point index of the gradient just evaluated: 0 = first point, L = last point of the trajectory.
+        // Interior points take the second half kick of step l and the first half kick of step l+1 (kick weight
+        // -1), the first and last point one half kick (-1/2); the position moves at every point but the last.
         float2 kw[TM / 2], dw[TM / 2], hv[TM / 2], hk[TM / 2];
+        {
+            const SlotBk& me = bk[lane];
+            const bool running = me.state == ST_RUN;
+            const unsigned m_l0 = __ballot_sync(HMC_FULL_MASK, running && me.l == 0);
+            const unsigned m_last = __ballot_sync(HMC_FULL_MASK, running && me.l == me.L);
+            const unsigned m_mid = __ballot_sync(HMC_FULL_MASK, running && me.l != 0 && me.l != me.L);
 #pragma unroll
-        for (int c = 0; c < TM / 2; ++c) {
-            const int b0 = cg * TM + 2 * c;
-            const float mid0 = (float)((m_mid >> b0) & 1u), mid1 = (float)((m_mid >> (b0 + 1)) & 1u);
-            const float mv0 = (float)(((m_mid | m_l0) >> b0) & 1u), mv1 = (float)(((m_mid | m_l0) >> (b0 + 1)) & 1u);
-            kw[c] = make_float2(-0.5f - 0.5f * mid0, -0.5f - 0.5f * mid1);
-            dw[c] = make_float2(mv0, mv1);
-            if (UDT) { kw[c].x *= dt0; kw[c].y *= dt0; dw[c].x *= dt0; dw[c].y *= dt0; }
-            hv[c] = make_float2(0.f, 0.f);
-            hk[c] = make_float2(0.f, 0.f);
+            for (int c = 0; c < TM / 2; ++c) {
+                const int b0 = cg * TM + 2 * c;
+                const float mid0 = (float)((m_mid >> b0) & 1u), mid1 = (float)((m_mid >> (b0 + 1)) & 1u);
+                const float mv0 = (float)(((m_mid | m_l0) >> b0) & 1u), mv1 = (float)(((m_mid | m_l0) >> (b0 + 1)) & 1u);
+                kw[c] = make_float2(-0.5f - 0.5f * mid0, -0.5f - 0.5f * mid1);
+                dw[c] = make_float2(mv0, mv1);
+                if (UDT) { kw[c].x *= dt0; kw[c].y *= dt0; dw[c].x *= dt0; dw[c].y *= dt0; }
+                hv[c] = make_float2(0.f, 0.f);
+                hk[c] = make_float2(0.f, 0.f);
+            }
+            (void)m_last;
         }
 #pragma unroll
         for (int jj = 0; jj < TN; ++jj) {
             const int j = jj * NDG + dg;
-            const bool jv = j < D;
+            const bool jv = FULL || (j < D);
             float dq[TM];
 #pragma unroll
             for (int i = 0; i < TM / 4; ++i)
@@ -393,69 +415,73 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
         }
         // ---- reduce the partial sums over the dimension groups (shared memory, fixed order => deterministic)
         if (active) {
-            float* r = red + (cg * NDG + dg) * 16;
-            *reinterpret_cast<float4*>(r + 0) = make_float4(hv[0].x, hv[0].y, hv[1].x, hv[1].y);
-            *reinterpret_cast<float4*>(r + 4) = make_float4(hv[2].x, hv[2].y, hv[3].x, hv[3].y);
-            *reinterpret_cast<float4*>(r + 8) = make_float4(hk[0].x, hk[0].y, hk[1].x, hk[1].y);
-            *reinterpret_cast<float4*>(r + 12) = make_float4(hk[2].x, hk[2].y, hk[3].x, hk[3].y);
+            float* r = red + (cg * NDG + dg) * G::RW;
+#pragma unroll
+            for (int c = 0; c < TM / 4; ++c) {
+                *reinterpret_cast<float4*>(r + 4 * c) = make_float4(hv[2 * c].x, hv[2 * c].y, hv[2 * c + 1].x, hv[2 * c + 1].y);
+                *reinterpret_cast<float4*>(r + TM + 4 * c) = make_float4(hk[2 * c].x, hk[2 * c].y, hk[2 * c + 1].x, hk[2 * c + 1].y);
+            }
         }
         __syncwarp();
 
         // ===== E. per-slot bookkeeping (lane s < NSLOT) ========================================================
-        if (lane < NSLOT && bk_state == ST_RUN) {
+        if (lane < NSLOT && bk[lane].state == ST_RUN) {
             const int s = lane, scg = s / TM, sc = s % TM;
-            const bool tr = a.phi_q && (a.chain_id0 + bk_m) == 0 && bk_it <= a.N_save_chain0;
-            if (bk_l != 0 && bk_l != bk_L) {
-                bk_l += 1;                                             // interior point: nothing to record
+            SlotBk b = bk[s];
+            const bool tr = a.phi_q && (a.chain_id0 + b.m) == 0 && b.it <= a.N_save_chain0;
+            if (b.l != 0 && b.l != b.L) {
+                b.l += 1;                                              // interior point: nothing to record
+                bk[s].l = b.l;
                 if (tr) {
-                    double* phi = a.phi_q + (size_t)(bk_it - 1) * a.L_high * 2;
-                    phi[2 * bk_l] = (double)(Ds[s] + mu_s[0]);
-                    if (D > 1) phi[2 * bk_l + 1] = (double)(Ds[QS + s] + mu_s[1]);
+                    double* phi = a.phi_q + (size_t)(b.it - 1) * a.L_high * 2;
+                    phi[2 * b.l] = (double)(Ds[s] + mu_s[0]);
+                    if (D > 1) phi[2 * b.l + 1] = (double)(Ds[QS + s] + mu_s[1]);
                 }
             } else {
                 float sv = 0.f, sk = 0.f;
 #pragma unroll
                 for (int d2 = 0; d2 < NDG; ++d2) {
-                    sv += red[(scg * NDG + d2) * 16 + sc];
-                    sk += red[(scg * NDG + d2) * 16 + 8 + sc];
+                    sv += red[(scg * NDG + d2) * G::RW + sc];
+                    sk += red[(scg * NDG + d2) * G::RW + TM + sc];
                 }
-                const double V = 0.5 * (double)sv + vconst;            // V(q) = 0.5 d.P d + const  (utils.py:213-218)
-                if (bk_l == 0) {
+                const double V = 0.5 * (double)sv + a.target.v_const;    // V(q) = 0.5 d.P d + const  (utils.py:213-218)
+                if (b.l == 0) {
                     // first point of a trajectory reached through a fresh gradient (chain start or after a rejection)
-                    if (bk_init) {                                     // samplers.py:416-420
-                        const double E0 = V + (double)bk_K0;
-                        a.E_chain[(size_t)bk_m * Lc] = E0;
-                        a.dE_chain[(size_t)bk_m * Lc] = 0.0;
-                        bk_Eprev = E0;
-                        bk_init = false;
+                    if (b.init) {                                      // samplers.py:416-420
+                        const double E0 = V + (double)b.K0;
+                        a.E_chain[(size_t)b.m * Lc] = E0;
+                        a.dE_chain[(size_t)b.m * Lc] = 0.0;
+                        b.Eprev = E0;
+                        b.init = 0;
                     }
-                    bk_Einit = V + (double)bk_Knew;                    // samplers.py:434-438
-                    if (bk_it >= a.warm_up_num) {
-                        const long idx = (bk_it - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)bk_m * Lc + idx] = bk_Einit;
-                        a.dE_chain[(size_t)bk_m * Lc + idx] = bk_Einit - bk_Eprev;
+                    b.Einit = V + (double)b.Knew;                      // samplers.py:434-438
+                    if (b.it >= a.warm_up_num) {
+                        const long idx = (b.it - a.warm_up_num) / a.thin_rate;
+                        a.E_chain[(size_t)b.m * Lc + idx] = b.Einit;
+                        a.dE_chain[(size_t)b.m * Lc + idx] = b.Einit - b.Eprev;
                     }
-                    bk_l = 1;
+                    b.l = 1;
                     if (tr) {
-                        double* phi = a.phi_q + (size_t)(bk_it - 1) * a.L_high * 2;
+                        double* phi = a.phi_q + (size_t)(b.it - 1) * a.L_high * 2;
                         phi[2] = (double)(Ds[s] + mu_s[0]);
                         if (D > 1) phi[3] = (double)(Ds[QS + s] + mu_s[1]);
                     }
                 } else {
                     // last point: Metropolis accept (samplers.py:455-472)
                     const double E_final = V + 0.5 * (double)sk;
-                    const double dE = E_final - bk_Einit;
-                    bk_Eprev = bk_Einit;                               // samplers.py:460
-                    const bool accepted = (dE < 0) || ((double)bk_lnu < -dE);      // samplers.py:462
+                    const double dE = E_final - b.Einit;
+                    b.Eprev = b.Einit;                                 // samplers.py:460
+                    const bool accepted = (dE < 0) || ((double)b.lnu < -dE);      // samplers.py:462
                     if (accepted) {
-                        if (bk_it >= a.warm_up_num) n_acc_post++; else n_acc_warm++;
-                        bk_V = V;
-                        bk_state = ST_ACC;
+                        if (b.it >= a.warm_up_num) n_acc_post++; else n_acc_warm++;
+                        b.V = V;
+                        b.state = ST_ACC;
                     } else {
-                        bk_state = ST_REJ;
+                        b.state = ST_REJ;
                     }
-                    if (tr) a.decision_chain[bk_it - 1] = accepted ? 1 : 0;
+                    if (tr) a.decision_chain[b.it - 1] = accepted ? 1 : 0;
                 }
+                bk[s] = b;
             }
         }
         __syncwarp();
@@ -472,21 +498,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
     }
 }
 
-template <int TN, int NDG, int NCG, int WARPS>
+template <int TM, int TN, int NDG, int NCG, int WARPS>
 size_t fast_smem_bytes(int D) {
-    using G = Geo<TN, NDG, NCG>;
-    return sizeof(float) * ((size_t)D * G::DP + 2 * G::DP + (size_t)WARPS * ((size_t)D * (G::QS + G::Q0S) + G::RED + G::STAGE));
+    using G = Geo<TM, TN, NDG, NCG>;
+    return sizeof(float) * ((size_t)D * G::DP + 2 * G::DP + (size_t)WARPS * ((size_t)D * G::QS + G::RED + G::STAGE + G::BK));
 }
 
-template <int TN, int NDG, int NCG, int WARPS, bool UDT>
+template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL>
 int launch_fast(const hmc_random_args& a, cudaStream_t stream) {
-    auto kern = hmc_random_fast_kernel<TN, NDG, NCG, WARPS, UDT>;
-    const size_t smem = fast_smem_bytes<TN, NDG, NCG, WARPS>(a.target.D);
+    auto kern = hmc_random_fast_kernel<TM, TN, NDG, NCG, WARPS, UDT, FULL>;
+    const size_t smem = fast_smem_bytes<TM, TN, NDG, NCG, WARPS>(a.target.D);
     HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     HMC_CUDA_CHECK(cudaGetDevice(&dev));
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int per_cta = WARPS * Geo<TN, NDG, NCG>::NSLOT;
+    const int per_cta = WARPS * Geo<TM, TN, NDG, NCG>::NSLOT;
     int grid = (a.Nchain + per_cta - 1) / per_cta;
     if (grid > sms) grid = sms;               // persistent: one CTA per SM, slots refill from the queue
     unsigned int* queue = (unsigned int*)a.state_g;   // scratch: work-queue head
@@ -511,6 +537,12 @@ bool hmc_random_fast_supported(const hmc_random_args& a, const char** why) {
 int hmc_random_run_fast(const hmc_random_args& a, cudaStream_t stream) {
     const int D = a.target.D;
     const bool udt = (a.flags & 1) != 0;
-    if (D > 80) return udt ? launch_fast<10, 10, 3, 8, true>(a, stream) : launch_fast<10, 10, 3, 8, false>(a, stream);
-    return udt ? launch_fast<10, 8, 4, 8, true>(a, stream) : launch_fast<10, 8, 4, 8, false>(a, stream);
+    const int variant = (a.flags >> 8) & 0xff;        // tuning knob (0 = default tile)
+    // measured on B200, Case 3c, 65,536 chains: 8x10 tile / 8 warps 1.39e9, 4x10 tile / 16 warps 1.38e9,
+    // 4x10 tile / 12 warps 1.49e9 gradient evals/s  =>  the 4x10 tile with 12 warps is the default.
+    if (D == 100 && udt && variant == 1) return launch_fast<8, 10, 10, 3, 8, true, true>(a, stream);
+    if (D == 100 && udt) return launch_fast<4, 10, 10, 3, 12, true, true>(a, stream);
+    if (D == 100) return udt ? launch_fast<8, 10, 10, 3, 8, true, true>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, true>(a, stream);
+    if (D > 80) return udt ? launch_fast<8, 10, 10, 3, 8, true, false>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, false>(a, stream);
+    return udt ? launch_fast<8, 10, 8, 4, 8, true, false>(a, stream) : launch_fast<8, 10, 8, 4, 8, false, false>(a, stream);
 }

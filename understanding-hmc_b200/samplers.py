@@ -12,6 +12,8 @@ Extra keyword-only constructor arguments (defaults keep the reference behaviour)
   chain_id0=0 / distributed=False (chains sharded over ranks; counters and moments are all-reduced),
   iter_block=None (iterations per kernel launch), target=None (explicit ``MVNSpec`` instead of probing V/dVdq).
 """
+import os
+
 from utils import *  # noqa: F401,F403  (samplers.py:1)
 import utils as _utils
 
@@ -300,6 +302,7 @@ class HMC_sampler(sampler):
         a.seed = self.seed
         a.target = tgt
         a.flags = 1 if np.ndim(self.dt) == 0 or np.all(np.asarray(self.dt) == np.asarray(self.dt).flat[0]) else 0
+        a.flags |= (int(os.environ.get("HMC_B200_TILE_VARIANT", "0")) & 0xff) << 8      # tuning knob
         a.q_start = keep["qs"].data_ptr()
         if self.draws is not None:
             keep["p_tape"] = torch.from_numpy(np.ascontiguousarray(self.draws["p_tape"], dtype=float)).to(dev)
