@@ -85,3 +85,36 @@ __device__ __forceinline__ T warp_sum(T v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HMC_FULL_MASK, v, o);
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-distributed vectors (lane l owns dimensions l, l+32, ...) used by the one-warp-per-chain kernels.
+// ---------------------------------------------------------------------------------------------------------
+// y = M x for a D x D matrix given by its transpose Mt[k][j] (row pitch Dp); x, y distributed over the warp
+// (lane l owns j = l, l+32, ...).  x is staged in a per-warp shared buffer and read back as a broadcast.
+template <typename T, int NJ>
+__device__ __forceinline__ void matvec_t(const T* __restrict__ Mt, int D, int Dp, const T (&x)[NJ], T (&y)[NJ],
+                                         int lane, T* __restrict__ xs) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) { y[i] = T(0); const int j = lane + 32 * i; if (j < D) xs[j] = x[i]; }
+    __syncwarp();
+#pragma unroll 2
+    for (int k = 0; k < D; ++k) {
+        const T xk = xs[k];
+        const T* row = Mt + (size_t)k * Dp;
+#pragma unroll
+        for (int i2 = 0; i2 < NJ; ++i2) {
+            const int j = lane + 32 * i2;
+            if (j < D) y[i2] = fma(row[j], xk, y[i2]);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T, int NJ>
+__device__ __forceinline__ double dot_warp(const T (&a)[NJ], const T (&b)[NJ]) {
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) s = fma(a[i], b[i], s);
+    return warp_sum<double>((double)s);
+}
+

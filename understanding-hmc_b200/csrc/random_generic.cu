@@ -7,35 +7,6 @@
 
 namespace {
 
-// y = M x for a D x D matrix given by its transpose Mt[k][j] (row pitch Dp); x, y distributed over the warp
-// (lane l owns j = l, l+32, ...).  x is staged in a per-warp shared buffer and read back as a broadcast.
-template <typename T, int NJ>
-__device__ __forceinline__ void matvec_t(const T* __restrict__ Mt, int D, int Dp, const T (&x)[NJ], T (&y)[NJ],
-                                         int lane, T* __restrict__ xs) {
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) { y[i] = T(0); const int j = lane + 32 * i; if (j < D) xs[j] = x[i]; }
-    __syncwarp();
-#pragma unroll 2
-    for (int k = 0; k < D; ++k) {
-        const T xk = xs[k];
-        const T* row = Mt + (size_t)k * Dp;
-#pragma unroll
-        for (int i2 = 0; i2 < NJ; ++i2) {
-            const int j = lane + 32 * i2;
-            if (j < D) y[i2] = fma(row[j], xk, y[i2]);
-        }
-    }
-    __syncwarp();
-}
-
-template <typename T, int NJ>
-__device__ __forceinline__ double dot_warp(const T (&a)[NJ], const T (&b)[NJ]) {
-    T s = T(0);
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) s = fma(a[i], b[i], s);
-    return warp_sum<double>((double)s);
-}
-
 template <typename T, int NJ>
 __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args a, int smem_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

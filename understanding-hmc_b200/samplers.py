@@ -372,7 +372,6 @@ class HMC_sampler(sampler):
         """NUTS sampler (samplers.py:495-808) on the GPU."""
         import torch
         lib = _L.load()
-        q_start = np.asarray(q_start)
         assert q_start.shape[0] == self.Nchain                                       # samplers.py:510
         if not self._cov_p_identity:
             raise NotImplementedError("NUTS CUDA kernel covers cov_p = I only (no CPU fallback)")
@@ -386,13 +385,13 @@ class HMC_sampler(sampler):
         self._E_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._dE_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._q_host = self._E_host = self._dE_host = None
-        qs = torch.from_numpy(np.ascontiguousarray(q_start, dtype=float)).to(device=dev, dtype=tdt).contiguous()
+        qs = self._to_device(torch, q_start, dev, tdt)
         state_q = torch.empty((Nc, D), dtype=tdt, device=dev)
         state_e = torch.zeros((Nc,), dtype=f64, device=dev)
         counters = torch.zeros((4,), dtype=torch.int64, device=dev)
         status = torch.zeros((Nc,), dtype=torch.int32, device=dev)
         nleap = torch.zeros((Nc,), dtype=torch.int64, device=dev)
-        scratch = torch.empty((Nc, 2 * (self.d_max + 1) + 2, tgt.D_pad), dtype=tdt, device=dev)
+        scratch = torch.zeros((Nc, 2 * (self.d_max + 1) + 7, tgt.D_pad), dtype=tdt, device=dev)
         a = _L.NutsArgs()
         a.dtype = _L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64
         a.kernel = _L.KERNELS[self.kernel]
