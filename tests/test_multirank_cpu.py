@@ -1,0 +1,75 @@
+"""World-size-2 gloo test (CPU) of the only exchange step on the path: the all-reduce of the split-chain moment
+and variogram partial sums for Rhat / ESS.  Each rank holds a contiguous slab of chains; the partials
+are produced here by numpy (on the GPU box they come from csrc/diag.cu), the reduce + finishing logic is the
+product code (utils._stats_from_partials)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import hmc_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, x, out_q):
+    sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import utils as U
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    Nchain = x.shape[0]
+    lo, hi = rank * Nchain // world, (rank + 1) * Nchain // world
+    xl = x[lo:hi]
+    n = xl.shape[1] // 2
+    halves = xl[:, :2 * n].reshape((hi - lo) * 2, n, xl.shape[2])
+
+    def moments_fn():
+        sd = np.std(halves, ddof=1, axis=1)
+        mu = np.mean(halves, axis=1)
+        return torch.from_numpy(np.stack([sd.sum(0), mu.sum(0), (mu ** 2).sum(0)]))
+
+    def variogram_fn(lag0, nl):
+        rows = [np.sum((halves[:, t:] - halves[:, :-t]) ** 2, axis=(0, 1)) for t in range(lag0, lag0 + nl)]
+        return torch.from_numpy(np.stack(rows))
+
+    R, ne = U._stats_from_partials(moments_fn, variogram_fn, n, x.shape[2], 2 * (hi - lo), group=None, lag_chunk=8)
+    out_q.put((rank, R, ne))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_rhat_ess_equals_single_rank(world):
+    import torch.multiprocessing as mp
+    rng = np.random.RandomState(0)
+    Nchain, N, D = 6, 80, 4
+    x = np.zeros((Nchain, N, D))
+    for t in range(1, N):
+        x[:, t] = 0.8 * x[:, t - 1] + rng.standard_normal((Nchain, D))
+    x += rng.standard_normal((Nchain, 1, D)) * 0.3          # between-chain spread so that B matters
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, x, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    R0, ne0 = O.convergence_stats(x, 1, 0)
+    for rank, R, ne in results:
+        np.testing.assert_allclose(R, R0, rtol=1e-10)
+        np.testing.assert_allclose(ne, ne0, rtol=1e-9)

@@ -114,25 +114,19 @@ def _finish_n_eff(var, V_rows, m, n, state):
     return all(st["done"] for st in state)
 
 
-def _device_stats(x, n, group=None, lag_chunk=32):
-    """x: CUDA tensor (Nchain_local, >=2n, D), float32/float64, last dim contiguous.  Returns (R, n_eff) numpy.
+def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32):
+    """Rhat / n_eff from per-rank partial sums (utils.py:107-157).
 
-    Per-device partial sums come from csrc/diag.cu; when torch.distributed is initialised they are all-reduced
-    (sum, float64) -- the only collective on the whole path."""
+    ``moments_fn()`` -> float64 tensor (3, D): sum_j std_j, sum_j mean_j, sum_j mean_j^2 over the LOCAL split
+    chains; ``variogram_fn(lag0, nl)`` -> float64 tensor (nl, D) of local variogram numerators.  When
+    torch.distributed is initialised (and ``group is not False``) the partials are all-reduced (sum) -- the only
+    collective on the whole path; everything after that is O(lags * D) host arithmetic."""
     import torch
     import torch.distributed as dist
-    lib = _L.load()
-    assert x.is_cuda and x.dim() == 3 and x.stride(2) == 1 and x.stride(1) == x.shape[2]
-    Nchain, _, D = x.shape
-    dtype = _L.HMC_F32 if x.dtype == torch.float32 else _L.HMC_F64
-    stride_chain = x.stride(0)
-    stream = _L.current_stream_ptr()
     distributed = dist.is_available() and dist.is_initialized() and (group is not False)
     grp = None if group in (None, False) else group
-
-    mom = torch.empty((3, D), dtype=torch.float64, device=x.device)
-    _L.check(lib.hmc_diag_moments(dtype, _L.ptr(x), Nchain, n, D, stride_chain, _L.ptr(mom), stream))
-    cnt = torch.tensor([2.0 * Nchain], dtype=torch.float64, device=x.device)
+    mom = moments_fn()
+    cnt = torch.tensor([float(m_local)], dtype=torch.float64, device=mom.device)
     if distributed:
         dist.all_reduce(mom, group=grp)
         dist.all_reduce(cnt, group=grp)
@@ -147,10 +141,9 @@ def _device_stats(x, n, group=None, lag_chunk=32):
     state = [dict(rho=[], t=1, done=False, started=False, sum_rho=0) for _ in range(D)]
     lag0 = 1
     max_lag = n - 1
-    buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
     while lag0 <= max_lag:
         nl = min(lag_chunk, max_lag - lag0 + 1)
-        _L.check(lib.hmc_diag_variogram(dtype, _L.ptr(x), Nchain, n, D, stride_chain, lag0, nl, _L.ptr(buf), stream))
+        buf = variogram_fn(lag0, nl)
         if distributed:
             dist.all_reduce(buf, group=grp)
         rows = buf[:nl].cpu().numpy()
@@ -158,12 +151,36 @@ def _device_stats(x, n, group=None, lag_chunk=32):
         if _finish_n_eff(var, V_rows, m, n, state):
             break
         lag0 += nl
-    for st in state:        # chains too short to ever start (n < 3): treat as sum_rho from what exists
+    for st in state:        # chains too short to ever start (n < 3): use what exists
         if not st["done"]:
             s = float(np.sum(st["rho"][:st["t"]]))
             st["sum_rho"] = 0 if s < 0 else s
     n_eff = np.array([m * n / (1 + 2 * st["sum_rho"]) for st in state], dtype=float)   # utils.py:157
     return R, n_eff
+
+
+def _device_stats(x, n, group=None, lag_chunk=32):
+    """x: CUDA tensor (Nchain_local, >=2n, D), float32/float64, last dim contiguous.  Returns (R, n_eff) numpy.
+    The per-device partial sums come from csrc/diag.cu through the C-ABI."""
+    import torch
+    lib = _L.load()
+    assert x.is_cuda and x.dim() == 3 and x.stride(2) == 1 and x.stride(1) == x.shape[2]
+    Nchain, _, D = x.shape
+    dtype = _L.HMC_F32 if x.dtype == torch.float32 else _L.HMC_F64
+    stride_chain = x.stride(0)
+
+    def moments_fn():
+        mom = torch.empty((3, D), dtype=torch.float64, device=x.device)
+        _L.check(lib.hmc_diag_moments(dtype, _L.ptr(x), Nchain, n, D, stride_chain, _L.ptr(mom), _L.current_stream_ptr()))
+        return mom
+
+    def variogram_fn(lag0, nl):
+        buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
+        _L.check(lib.hmc_diag_variogram(dtype, _L.ptr(x), Nchain, n, D, stride_chain, lag0, nl, _L.ptr(buf),
+                                        _L.current_stream_ptr()))
+        return buf
+
+    return _stats_from_partials(moments_fn, variogram_fn, n, D, 2 * Nchain, group=group, lag_chunk=lag_chunk)
 
 
 def convergence_stats(q_chain, thin_rate=5, warm_up_num=0, group=None):
