@@ -132,7 +132,7 @@ class ClockSampler(threading.Thread):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
@@ -210,15 +210,15 @@ def main():
     counters = run["counters"]
     stream = L.current_stream_ptr()
     log("buffers ready (%d chains, %d iterations)" % (Nc, Niter))
+    sampler_thread = ClockSampler(local_rank) if rank == 0 else None      # samples through warm-up + timed region
+    if sampler_thread:
+        sampler_thread.start()
     for i in range(W):
         run["args"].iter_begin, run["args"].iter_end = i * IB, (i + 1) * IB
         L.check(lib.hmc_random_run(run["args"], stream))
     barrier()
     log("warm-up done")
     c0 = counters.clone()
-    sampler_thread = ClockSampler(local_rank) if rank == 0 else None
-    if sampler_thread:
-        sampler_thread.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
@@ -249,7 +249,7 @@ def main():
     flop = executed_local * 2.0 * D * D
     achieved = flop / (ms * 1e-3) / 1e12
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    roofline = {"bound": "fp32_ffma", "kernel": "hmc_random_fast_kernel<10,10,3,8>", "achieved": achieved,
+    roofline = {"bound": "fp32_ffma", "kernel": "hmc_random_fast_kernel<TM=4,TN=10,NDG=10,NCG=3,WARPS=12>", "achieved": achieved,
                 "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak.value / 1e12),
                 "peak_source": "FFMA microbenchmark (hmc_ffma_peak) measured in this run; nominal 2*128*%d SMs*1.965 GHz = %.1f"
                                % (sms, 2 * 128 * sms * 1.965e9 / 1e12),
