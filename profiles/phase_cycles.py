@@ -1,0 +1,36 @@
+"""Per-phase cycle accounting of the fused kernel (debug build with -DHMC_PROFILE_PHASES, see csrc/random_fast.cu)."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
+import numpy as np, torch
+import hmc_b200_lib as L
+L.LIB_PATH = os.path.join(ROOT, "understanding-hmc_b200", "bin", "libhmc_b200_prof.so")
+import samplers as S
+from oracle import hmc_oracle as O
+D, Nc, IB = 100, int(sys.argv[1]) if len(sys.argv) > 1 else 28416, int(sys.argv[2]) if len(sys.argv) > 2 else 20
+spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
+lib = L.load()
+lib.hmc_debug_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+for variant in (1, 2, 0):
+    os.environ["HMC_B200_TILE_VARIANT"] = str(variant)
+    H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB * 2, sampler_type="Random", dt=0.1, L_low=5, L_high=20,
+                      dtype="float32", kernel="fast", seed=1, target=spec)
+    run = H.prepare_random(q0)
+    run["args"].iter_begin, run["args"].iter_end = 0, IB
+    L.check(lib.hmc_random_run(run["args"], L.current_stream_ptr())); torch.cuda.synchronize()
+    lib.hmc_debug_phase_cycles(None, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run["args"].iter_begin, run["args"].iter_end = IB, 2 * IB
+    L.check(lib.hmc_random_run(run["args"], L.current_stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    out = (C.c_ulonglong * 8)()
+    lib.hmc_debug_phase_cycles(out, 0)
+    v = np.array(list(out), dtype=float)
+    steps = v[5]
+    print("variant %d (%s): %.2f ms; warp-steps %d; cycles per warp-step: service %.0f, gradient %.0f, update %.0f, bookkeeping %.0f, total %.0f"
+          % (variant, {1: "8x10 tile, 8 warps", 2: "8x10 tile, 8 warps, ping-pong pairs", 0: "4x10 tile, 12 warps"}[variant], e0.elapsed_time(e1), steps,
+             v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps))
+    print("   inside service, cycles per warp-step: move/store/refill %.0f, gen_momentum %.0f, rest (bookkeeping + register refresh) %.0f"
+          % (v[6] / steps, v[7] / steps, (v[0] - v[6] - v[7]) / steps))

@@ -51,6 +51,67 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_kernel(const T* __r
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
 }
 
+
+// float32 stream, D % 4 == 0: one thread owns FOUR adjacent dimensions of one split chain and walks the time axis
+// with 128-bit loads (8 rows in flight per thread), so that enough bytes are in flight to saturate HBM.
+__global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const float* __restrict__ q, long Nchain, long n, int D,
+                                                                          long stride_chain, int spb, double* __restrict__ out) {
+    extern __shared__ double sm[];   // [3][D]
+    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int D4 = D >> 2;
+    const int dq = threadIdx.x % D4;
+    const int sl = threadIdx.x / D4;
+    double s_std[4] = {0, 0, 0, 0}, s_mean[4] = {0, 0, 0, 0}, s_mean2[4] = {0, 0, 0, 0};
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const float4* x = reinterpret_cast<const float4*>(q + (s >> 1) * stride_chain + (s & 1) * n * D) + dq;
+            const float4 x0 = x[0];
+            // float partial sums over blocks of 8 rows (shifted by the first sample), float64 across blocks
+            double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+            long i = 0;
+            for (; i + 8 <= n; i += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = x[(i + u) * D4];
+                float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float e0 = v[u].x - x0.x, e1 = v[u].y - x0.y, e2 = v[u].z - x0.z, e3 = v[u].w - x0.w;
+                    pa[0] += e0; pa[1] += e1; pa[2] += e2; pa[3] += e3;
+                    pb[0] = fmaf(e0, e0, pb[0]); pb[1] = fmaf(e1, e1, pb[1]); pb[2] = fmaf(e2, e2, pb[2]); pb[3] = fmaf(e3, e3, pb[3]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { a[c] += (double)pa[c]; b[c] += (double)pb[c]; }
+            }
+            for (; i < n; ++i) {
+                const float4 v = x[i * D4];
+                const double e[4] = {(double)v.x - x0.x, (double)v.y - x0.y, (double)v.z - x0.z, (double)v.w - x0.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { a[c] += e[c]; b[c] += e[c] * e[c]; }
+            }
+            const double xs[4] = {(double)x0.x, (double)x0.y, (double)x0.z, (double)x0.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double mean_s = a[c] / (double)n;
+                double var = (b[c] - (double)n * mean_s * mean_s) / (double)(n - 1);   // ddof = 1 (utils.py:111)
+                if (var < 0.0) var = 0.0;
+                const double mean = mean_s + xs[c];
+                s_std[c] += sqrt(var); s_mean[c] += mean; s_mean2[c] += mean * mean;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            atomicAdd(&sm[4 * dq + c], s_std[c]);
+            atomicAdd(&sm[D + 4 * dq + c], s_mean[c]);
+            atomicAdd(&sm[2 * D + 4 * dq + c], s_mean2[c]);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+}
+
 // Lags t = lag0 + k, k < NL.  For every i the pair (x[i], x[i - lag0 - k]) contributes (x[i]-x[i-lag0-k])^2.
 // The last NL delayed values live in a register window addressed with compile-time indices (the time loop is
 // unrolled by NL); float partial sums are flushed into float64 every NL steps.
@@ -156,7 +217,12 @@ extern "C" int hmc_diag_moments(int32_t dtype, const void* q, int64_t Nchain, in
     const int grid = grid_for(2 * Nchain, spb);
     const size_t smem = sizeof(double) * 3 * D;
     HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, smem, stream));
-    if (dtype == HMC_F32)
+    const bool vec4 = dtype == HMC_F32 && (D % 4) == 0 && (stride_chain % 4) == 0 && (n * D) % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(q) % 16) == 0;
+    if (vec4) {
+        const int spb4 = kDiagThreads / (D / 4);
+        diag_moments_f32x4_kernel<<<grid_for(2 * Nchain, spb4), kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb4, out3xD);
+    } else if (dtype == HMC_F32)
         diag_moments_kernel<float><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, out3xD);
     else
         diag_moments_kernel<double><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, out3xD);

@@ -18,6 +18,16 @@
 // HBM sees only the stored sample / energy stream and the final chain state.
 #include "hmc_common.cuh"
 
+// per-phase cycle accounting for profiles/phase_cycles.py (debug build only)
+#ifdef HMC_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[8];
+#define PH_T(x) const long long x = clock64()
+#define PH_ADD(i, a, b) ph[i] += (b) - (a)
+#else
+#define PH_T(x)
+#define PH_ADD(i, a, b)
+#endif
+
 namespace {
 
 
@@ -115,7 +125,7 @@ __device__ __noinline__ void gen_momentum(const GenArgs a, long m, uint64_t gid,
     __syncwarp();
 }
 
-template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL>
+template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL, bool PINGPONG>
 __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
     using G = Geo<TM, TN, NDG, NCG>;
     static_assert(TM % 4 == 0 && G::NSLOT <= 32, "tile");
@@ -126,7 +136,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
     float* Ps = sm;                       // [D][DP]   Ps[k][dg*TN + jj] = P[k][jj*NDG + dg]
     float* mu_s = Ps + D * DP;            // [DP]
     float* dt_s = mu_s + DP;              // [DP]
-    float* wbase = dt_s + DP + (size_t)warp * (D * QS + G::RED + G::STAGE + G::BK);
+    int* done_flags = reinterpret_cast<int*>(dt_s + DP);   // [32] per-warp 'no chain left' flags (ping-pong pairs)
+    float* wbase = dt_s + DP + 32 + (size_t)warp * (D * QS + G::RED + G::STAGE + G::BK);
     float* Ds = wbase;                    // [D][QS]   live positions (shifted by mu)
     float* red = Ds + D * QS;             // [32][16]  per-lane partial sums
     float* stage = red + G::RED;          // momentum staging
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             const int j = (c % TN) * NDG + c / TN;          // lane-order column -> dimension
             Ps[t] = (j < D) ? Ft[(size_t)k * Dpad + j] : 0.f;
         }
+        if (threadIdx.x < 32) done_flags[threadIdx.x] = 0;
         for (int t = threadIdx.x; t < DP; t += blockDim.x) {
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
@@ -174,10 +186,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
     ga.D = D; ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
     __syncwarp();
 
-    while (true) {
+#ifdef HMC_PROFILE_PHASES
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    // ---------------------------------------------------------------------------------------------------------
+    // The three phases of one pass over the warp's slots.
+    // ---------------------------------------------------------------------------------------------------------
+    auto do_service = [&]() {
+        PH_T(tA);
         // ===== A. service every slot that finished a trajectory or needs a chain (warp-uniform loop) ==========
         unsigned need = __ballot_sync(HMC_FULL_MASK, bk[lane].state >= ST_NEED_CHAIN);
         while (need) {
+            PH_T(tS0);
             const int s = __ffs(need) - 1;
             need &= need - 1;
             const int scg = s / TM, sc = s % TM;
@@ -267,11 +287,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     bk[s].init = 0;
                 }
             }
+            PH_T(tS1);
+            PH_ADD(6, tS0, tS1);
             // ---- start iteration it+1: momentum refresh (samplers.py:431), trajectory length (:441), uniform (:461)
             const int itn = it + 1;
             const uint64_t gid = (uint64_t)(a.chain_id0 + m);
             float ksum, lnun; int Ln;
             gen_momentum(ga, m, gid, itn, lane, stage, &ksum, &Ln, &lnun);
+            PH_T(tS2);
+            PH_ADD(7, tS1, tS2);
             const bool go = (kind == ST_ACC);      // gradient at the accepted point is still in g: kick and drift now
             const bool tr = a.phi_q && gid == 0 && itn <= a.N_save_chain0;
             if (lane == s) {
@@ -331,9 +355,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             }
         }
 
-        // ===== B. done when no slot runs ====================================================================
-        if (__ballot_sync(HMC_FULL_MASK, bk[lane].state == ST_RUN) == 0u) break;
-
+        PH_T(tB);
+        PH_ADD(0, tA, tB);
+    };
+    auto do_gradient = [&]() {
+        PH_T(tB);
         // ===== C. gradient  g[c][j] = sum_k d[k][c] P[k][j]  ==================================================
 #pragma unroll
         for (int c = 0; c < TM / 2; ++c)
@@ -361,7 +387,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             }
         }
         __syncwarp();
-
+        PH_T(tD);
+        PH_ADD(1, tB, tD);
+    };
+    auto do_update = [&]() {
+        PH_T(tD);
         // ===== D. leapfrog update of the lane's tile (samplers.py:835-837) + energy partial sums ================
         // point index of the gradient just evaluated: 0 = first point, L = last point of the trajectory.
         // Interior points take the second half kick of step l and the first half kick of step l+1 (kick weight
@@ -423,7 +453,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             }
         }
         __syncwarp();
-
+        PH_T(tE);
+        PH_ADD(2, tD, tE);
         // ===== E. per-slot bookkeeping (lane s < NSLOT) ========================================================
         if (lane < NSLOT && bk[lane].state == ST_RUN) {
             const int s = lane, scg = s / TM, sc = s % TM;
@@ -485,7 +516,51 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             }
         }
         __syncwarp();
+        PH_T(tF);
+        PH_ADD(3, tE, tF);
+#ifdef HMC_PROFILE_PHASES
+        ph[5] += 1;
+#endif
+    };
+    auto any_running = [&]() -> bool { return __ballot_sync(HMC_FULL_MASK, bk[lane].state == ST_RUN) != 0u; };
+
+    do_service();                              // initial fill of the slots
+    bool running = any_running();
+    if constexpr (PINGPONG) {
+        // Warps w and w+4 share a scheduler (warp id mod 4).  Left alone they lock in phase -- both in the
+        // gradient loop (sharing the FMA pipe), then both in the latency-bound update/service code (FMA pipe idle;
+        // measured: profiles/phase_cycles.py).  A 64-thread named barrier per pair makes them alternate instead:
+        // on every tick one warp of the pair runs its gradient loop while the other runs update + service.
+        static_assert(WARPS == 8, "ping-pong pairs warps w and w+4");
+        const int role = warp >> 2, pair = warp & 3;
+        volatile int* done = reinterpret_cast<volatile int*>(done_flags);
+        bool have_grad = false;
+        for (int tick = 0;; ++tick) {
+            PH_T(tT0);
+            if (running) {
+                if ((tick & 1) == role) { do_gradient(); have_grad = true; }
+                else if (have_grad) { do_update(); do_service(); have_grad = false; running = any_running(); }
+            }
+            if (lane == 0) done[warp] = running ? 0 : 1;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+            PH_T(tT2);
+            PH_ADD(4, tT0, tT2);
+            if (done[warp] && done[warp ^ 4] && !have_grad) break;
+        }
+    } else {
+        while (running) {
+            PH_T(tL0);
+            do_gradient();
+            do_update();
+            do_service();
+            running = any_running();
+            PH_T(tL1);
+            PH_ADD(4, tL0, tL1);
+        }
     }
+#ifdef HMC_PROFILE_PHASES
+    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)ph[i]);
+#endif
 
     // ---- counters (samplers.py:484-488 numerators; sum L, sum L^2 for N_total_steps) ---------------------------
     if (a.counters) {
@@ -501,12 +576,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
 template <int TM, int TN, int NDG, int NCG, int WARPS>
 size_t fast_smem_bytes(int D) {
     using G = Geo<TM, TN, NDG, NCG>;
-    return sizeof(float) * ((size_t)D * G::DP + 2 * G::DP + (size_t)WARPS * ((size_t)D * G::QS + G::RED + G::STAGE + G::BK));
+    return sizeof(float) * ((size_t)D * G::DP + 2 * G::DP + 32 + (size_t)WARPS * ((size_t)D * G::QS + G::RED + G::STAGE + G::BK));
 }
 
-template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL>
+template <int TM, int TN, int NDG, int NCG, int WARPS, bool UDT, bool FULL, bool PINGPONG = false>
 int launch_fast(const hmc_random_args& a, cudaStream_t stream) {
-    auto kern = hmc_random_fast_kernel<TM, TN, NDG, NCG, WARPS, UDT, FULL>;
+    auto kern = hmc_random_fast_kernel<TM, TN, NDG, NCG, WARPS, UDT, FULL, PINGPONG>;
     const size_t smem = fast_smem_bytes<TM, TN, NDG, NCG, WARPS>(a.target.D);
     HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
@@ -523,6 +598,14 @@ int launch_fast(const hmc_random_args& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+#ifdef HMC_PROFILE_PHASES
+extern "C" int hmc_debug_phase_cycles(unsigned long long* out8, int reset) {
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); return 0; }
+    cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8);
+    return 0;
+}
+#endif
 
 bool hmc_random_fast_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
@@ -541,6 +624,7 @@ int hmc_random_run_fast(const hmc_random_args& a, cudaStream_t stream) {
     // measured on B200, Case 3c, 65,536 chains: 8x10 tile / 8 warps 1.39e9, 4x10 tile / 16 warps 1.38e9,
     // 4x10 tile / 12 warps 1.49e9 gradient evals/s  =>  the 4x10 tile with 12 warps is the default.
     if (D == 100 && udt && variant == 1) return launch_fast<8, 10, 10, 3, 8, true, true>(a, stream);
+    if (D == 100 && udt && variant == 2) return launch_fast<8, 10, 10, 3, 8, true, true, true>(a, stream);
     if (D == 100 && udt) return launch_fast<4, 10, 10, 3, 12, true, true>(a, stream);
     if (D == 100) return udt ? launch_fast<8, 10, 10, 3, 8, true, true>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, true>(a, stream);
     if (D > 80) return udt ? launch_fast<8, 10, 10, 3, 8, true, false>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, false>(a, stream);
