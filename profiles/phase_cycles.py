@@ -12,7 +12,7 @@ spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
 q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
 lib = L.load()
 lib.hmc_debug_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
-for variant in (1, 2, 0):
+for variant in (1, 2, 3, 0):
     os.environ["HMC_B200_TILE_VARIANT"] = str(variant)
     H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB * 2, sampler_type="Random", dt=0.1, L_low=5, L_high=20,
                       dtype="float32", kernel="fast", seed=1, target=spec)
@@ -30,7 +30,7 @@ for variant in (1, 2, 0):
     v = np.array(list(out), dtype=float)
     steps = v[5]
     print("variant %d (%s): %.2f ms; warp-steps %d; cycles per warp-step: service %.0f, gradient %.0f, update %.0f, bookkeeping %.0f, total %.0f"
-          % (variant, {1: "8x10 tile, 8 warps", 2: "8x10 tile, 8 warps, ping-pong pairs", 0: "4x10 tile, 12 warps"}[variant], e0.elapsed_time(e1), steps,
+          % (variant, {1: "8x10 tile, 8 warps", 2: "8x10 tile, 8 warps, ping-pong pairs", 3: "8x10 tile, 4 warps (one per scheduler)", 0: "4x10 tile, 12 warps"}[variant], e0.elapsed_time(e1), steps,
              v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps))
     print("   inside service, cycles per warp-step: move/store/refill %.0f, gen_momentum %.0f, rest (bookkeeping + register refresh) %.0f"
           % (v[6] / steps, v[7] / steps, (v[0] - v[6] - v[7]) / steps))

@@ -1,4 +1,4 @@
-// Fused random-trajectory HMC kernel, FP32, 40 < D <= 100, identity momentum metric (the production path).
+// Fused random-trajectory HMC kernel, FP32, 20 < D <= 128, identity momentum metric (the production path).
 //
 // Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839) with one
 // gradient evaluation per leapfrog step (the second gradient of step l is the first of step l+1).
@@ -94,7 +94,7 @@ __device__ __noinline__ void gen_momentum(const GenArgs a, long m, uint64_t gid,
         }
     } else {
         const int nslot = (D + 3) >> 2;
-        const bool scalar_lane = (lane == nslot);        // nslot <= 25 < 32 for D <= 100
+        const bool scalar_lane = (lane == nslot);        // a free lane exists while nslot < 32 (D <= 124)
         const uint32_t hi = (uint32_t)(gid >> 32) << 8;
         const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)iter, scalar_lane ? 0u : (uint32_t)lane,
                                         (scalar_lane ? (uint32_t)HMC_STREAM_SCALAR : (uint32_t)HMC_STREAM_MOMENTUM) | hi,
@@ -116,8 +116,14 @@ __device__ __noinline__ void gen_momentum(const GenArgs a, long m, uint64_t gid,
         }
         const int Ls = a.L_low + (int)__umulhi(r.x, (uint32_t)(a.L_high - a.L_low));
         const float ls = logf(((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-08f);
-        Lv = __shfl_sync(HMC_FULL_MASK, Ls, nslot);
-        lv = __shfl_sync(HMC_FULL_MASK, ls, nslot);
+        if (nslot < 32) {
+            Lv = __shfl_sync(HMC_FULL_MASK, Ls, nslot);
+            lv = __shfl_sync(HMC_FULL_MASK, ls, nslot);
+        } else if (iter >= 1) {                              // all 32 lanes carry momentum slots: separate scalar draw
+            double uu;
+            hmc_scalar_draws(a.seed, gid, (uint32_t)iter, a.L_low, a.L_high, &Lv, &uu);
+            lv = logf((float)uu);
+        }
     }
     *sumsq = warp_sum<float>(s);
     *L = Lv;
@@ -610,7 +616,7 @@ extern "C" int hmc_debug_phase_cycles(unsigned long long* out8, int reset) {
 bool hmc_random_fast_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
     if (a.target.Mit || a.target.Pt || a.target.Lct) { *why = "identity momentum metric only"; return false; }
-    if (a.target.D > 100 || a.target.D <= 40) { *why = "40 < D <= 100 in this build"; return false; }
+    if (a.target.D > 128 || a.target.D <= 20) { *why = "20 < D <= 128 in this build"; return false; }
     if (a.iter_end <= a.iter_begin) { *why = "needs at least one iteration"; return false; }
     if (!a.state_g) { *why = "state_g scratch required"; return false; }
     return true;
@@ -625,8 +631,11 @@ int hmc_random_run_fast(const hmc_random_args& a, cudaStream_t stream) {
     // 4x10 tile / 12 warps 1.49e9 gradient evals/s  =>  the 4x10 tile with 12 warps is the default.
     if (D == 100 && udt && variant == 1) return launch_fast<8, 10, 10, 3, 8, true, true>(a, stream);
     if (D == 100 && udt && variant == 2) return launch_fast<8, 10, 10, 3, 8, true, true, true>(a, stream);
+    if (D == 100 && udt && variant == 3) return launch_fast<8, 10, 10, 3, 4, true, true>(a, stream);   // probe: 1 warp per scheduler
     if (D == 100 && udt) return launch_fast<4, 10, 10, 3, 12, true, true>(a, stream);
     if (D == 100) return udt ? launch_fast<8, 10, 10, 3, 8, true, true>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, true>(a, stream);
-    if (D > 80) return udt ? launch_fast<8, 10, 10, 3, 8, true, false>(a, stream) : launch_fast<8, 10, 10, 3, 8, false, false>(a, stream);
-    return udt ? launch_fast<8, 10, 8, 4, 8, true, false>(a, stream) : launch_fast<8, 10, 8, 4, 8, false, false>(a, stream);
+    if (D > 100) return udt ? launch_fast<4, 8, 16, 2, 12, true, false>(a, stream) : launch_fast<4, 8, 16, 2, 12, false, false>(a, stream);
+    if (D > 80) return udt ? launch_fast<4, 10, 10, 3, 12, true, false>(a, stream) : launch_fast<4, 10, 10, 3, 12, false, false>(a, stream);
+    if (D > 40) return udt ? launch_fast<4, 10, 8, 4, 12, true, false>(a, stream) : launch_fast<4, 10, 8, 4, 12, false, false>(a, stream);
+    return udt ? launch_fast<4, 10, 4, 8, 12, true, false>(a, stream) : launch_fast<4, 10, 4, 8, 12, false, false>(a, stream);
 }
