@@ -275,6 +275,60 @@ __global__ void __launch_bounds__(WARPS * 32) warp_generic_kernel(float* out, in
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+
+// ---- (F) like (E) with TM=8, TN=10 but explicit register double buffering of the operands (loads of step k+1
+// issued before the FMAs of step k): how efficient is the loop with ONE warp per scheduler?
+template <int WARPS, int UNR>
+__global__ void __launch_bounds__(WARPS * 32) warp_db_kernel(float* out, int steps) {
+    constexpr int TM = 8, TN = 10, NCGW = 3, NDGW = 10, K = 100, QS = 28, PS = NDGW * TN;
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;
+    float* Q = sm + K * PS + (threadIdx.x >> 5) * (K * QS);
+    for (int t = threadIdx.x; t < K * PS; t += blockDim.x) P[t] = 1e-3f * ((t * 7) % 13 - 6);
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < K * QS; t += 32) Q[t] = 1e-2f * ((t * 5) % 11 - 5);
+    __syncthreads();
+    const bool active = lane < NCGW * NDGW;
+    const int cg = active ? lane / NDGW : 0, dg = active ? lane % NDGW : 0;
+    float2 acc[TM / 2][TN];
+#pragma unroll
+    for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[c][j] = make_float2(0.f, 0.f);
+    const float* qp = Q + cg * TM;
+    const float* pp = P + dg * TN;
+    auto load = [&](int k, float (&qv)[TM], float (&pv)[TN]) {
+#pragma unroll
+        for (int i = 0; i < TM / 4; ++i) *reinterpret_cast<float4*>(&qv[4 * i]) = *reinterpret_cast<const float4*>(qp + k * QS + 4 * i);
+#pragma unroll
+        for (int i = 0; i < TN / 2; ++i) *reinterpret_cast<float2*>(&pv[2 * i]) = *reinterpret_cast<const float2*>(pp + k * PS + 2 * i);
+    };
+    auto fmas = [&](const float (&qv)[TM], const float (&pv)[TN]) {
+#pragma unroll
+        for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) ffma2(acc[c][j], make_float2(qv[2 * c], qv[2 * c + 1]), make_float2(pv[j], pv[j]));
+    };
+    for (int s = 0; s < steps; ++s) {
+        float qa[TM], pa[TN], qb[TM], pb[TN];
+        load(0, qa, pa);
+#pragma unroll UNR
+        for (int k = 0; k < K; k += 2) {
+            load(k + 1, qb, pb);
+            fmas(qa, pa);
+            load((k + 2 < K) ? k + 2 : 0, qa, pa);
+            fmas(qb, pb);
+        }
+        if (acc[0][0].x == 123.456f) Q[lane] = acc[0][1].y;
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int c = 0; c < TM / 2; ++c)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) r += acc[c][j].x + acc[c][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 template <typename F>
 double time_ms(F launch, int reps = 3) {
     cudaEvent_t e0, e1;
@@ -393,7 +447,23 @@ int main() {
         RUN_E(8, 8, 4, 8, 8)
         RUN_E(8, 8, 4, 8, 12)
         RUN_E(8, 12, 4, 8, 8)
-        RUN_E(4, 25, 8, 4, 8)
+    }
+
+    {
+        RUN_E(8, 10, 3, 10, 4)
+#define RUN_F(W, UNR)                                                                                          \
+        {                                                                                                    \
+            const size_t smem = sizeof(float) * (100 * 100 + W * 100 * 28);                                  \
+            auto kf = warp_db_kernel<W, UNR>;                                                                \
+            CK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            double ms = time_ms([&] { kf<<<sms, W * 32, smem>>>(out, steps); });                             \
+            printf("(F) TM=8 TN=10 double-buffered, %d warps, unroll %d: %.2f TFLOP/s useful\n", W, UNR,      \
+                   2.0 * 100 * 100 * 24.0 * W * sms * steps / (ms * 1e-3) / 1e12);                           \
+        }
+        RUN_F(4, 1)
+        RUN_F(4, 2)
+        RUN_F(8, 1)
+        RUN_F(8, 2)
     }
     CK(cudaFree(out));
     return 0;

@@ -374,9 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
         {
             const float* qp = Ds + cg * TM;
             const float* pp = Ps + dg * TN;
-#pragma unroll 2
-            for (int k = 0; k < D; ++k) {
-                float qv[TM], pv[TN];
+            auto load = [&](int k, float (&qv)[TM], float (&pv)[TN]) {
 #pragma unroll
                 for (int i = 0; i < TM / 4; ++i) *reinterpret_cast<float4*>(&qv[4 * i]) = *reinterpret_cast<const float4*>(qp + k * QS + 4 * i);
                 if constexpr (TN % 4 == 0) {
@@ -386,10 +384,32 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
 #pragma unroll
                     for (int i = 0; i < TN / 2; ++i) *reinterpret_cast<float2*>(&pv[2 * i]) = *reinterpret_cast<const float2*>(pp + k * DP + 2 * i);
                 }
+            };
+            auto fmas = [&](const float (&qv)[TM], const float (&pv)[TN]) {
 #pragma unroll
                 for (int c = 0; c < TM / 2; ++c)
 #pragma unroll
                     for (int j = 0; j < TN; ++j) g[c][j] = fma2(make_float2(qv[2 * c], qv[2 * c + 1]), bc2(pv[j]), g[c][j]);
+            };
+            if constexpr (PINGPONG && FULL) {
+                // explicit register double buffering: with one warp per scheduler in the loop (ping-pong) the
+                // shared-memory latency is otherwise exposed at every iteration (probe F: 78 % vs 68 % of peak)
+                float qa[TM], pa[TN], qb[TM], pb[TN];
+                load(0, qa, pa);
+#pragma unroll 1
+                for (int k = 0; k < D; k += 2) {
+                    load(k + 1, qb, pb);
+                    fmas(qa, pa);
+                    load((k + 2 < D) ? k + 2 : 0, qa, pa);
+                    fmas(qb, pb);
+                }
+            } else {
+#pragma unroll 2
+                for (int k = 0; k < D; ++k) {
+                    float qv[TM], pv[TN];
+                    load(k, qv, pv);
+                    fmas(qv, pv);
+                }
             }
         }
         __syncwarp();
