@@ -99,26 +99,36 @@ def cpu_reference(nchain_per_proc=8, niter=60, cores=None):
 
 
 # ------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler(object):
+    """Samples clocks / throttle reasons during the timed region with one `nvidia-smi -lms 100` process
+    (the profiling recipe's clocks line)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        threading.Thread.__init__(self, daemon=True)
         self.index = index
-        self.stop_flag = False
+        self.proc = None
         self.rows = []
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = b""
+        for line in out.decode(errors="ignore").splitlines():
+            self.rows.append([x.strip() for x in line.split(",")])
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -227,7 +237,7 @@ def main():
     ev1.record()
     barrier()
     if sampler_thread:
-        sampler_thread.stop_flag = True
+        sampler_thread.stop()
     ms = ev0.elapsed_time(ev1)
     log("timed region done: %.1f ms for %d steps" % (ms, K))
     dc = (counters - c0).cpu().numpy().astype(np.int64)

@@ -268,3 +268,33 @@ def test_fast_kernel_other_dimensions_match_generic(D, rho):
     assert abs(F.accept_R - G.accept_R) < 5e-3
     np.testing.assert_allclose(F.E_chain[:, 0, 0], G.E_chain[:, 0, 0], rtol=2e-5)
     assert np.all(np.isfinite(F.q_chain))
+
+
+def test_generic_kernel_large_dimension_matches_oracle():
+    """D = 1024 (BASELINE config 5 shape): the generic kernel's widest instantiation, precision matrix read from
+    HBM/L2.  Teacher-forced single iterations against the float64 oracle, float64 and float32."""
+    import samplers as S
+    D, B = 1024, 6
+    rng = np.random.RandomState(7)
+    lam = np.exp(rng.uniform(np.log(0.05), np.log(100.0), D))        # SURVEY 8d-5: log-uniform spectrum
+    Qm, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    cov = (Qm * lam) @ Qm.T
+    cov = 0.5 * (cov + cov.T)
+    tgt = O.MVNTarget(np.zeros(D), cov)
+    q_init = rng.standard_normal((B, D)) * np.sqrt(lam).mean()
+    p_tape = np.zeros((B, 2, D)); p_tape[:, 1] = rng.standard_normal((B, D))
+    L_tape = rng.randint(20, 60, size=(B, 1)).astype(np.int32)
+    u_tape = np.full((B, 1), 1e-300)
+    want = np.zeros((B, D))
+    for b in range(B):
+        q, p = q_init[b].copy(), p_tape[b, 1].copy()
+        for _ in range(int(L_tape[b, 0])):
+            p, q = O.leap_frog(p, q, 0.1, np.eye(D), tgt.dVdq)
+        want[b] = q
+    spec = S.MVNSpec(np.zeros(D), tgt.inv_cov0, tgt.const)
+    for dtype, tol in (("float64", 1e-9), ("float32", 2e-3)):
+        H = S.HMC_sampler(D, None, None, Nchain=B, Niter=1, sampler_type="Random", dt=0.1, L_low=20, L_high=60,
+                          dtype=dtype, kernel="generic", target=spec, draws=dict(p_tape=p_tape, L_tape=L_tape, u_tape=u_tape))
+        H.gen_sample(q_init, verbose=False, quiet=True)
+        rel = np.linalg.norm(H.q_chain[:, 1] - want, axis=1) / np.linalg.norm(q_init, axis=1)
+        assert rel.max() < tol, (dtype, rel.max())
