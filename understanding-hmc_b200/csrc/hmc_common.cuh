@@ -87,24 +87,98 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Warp-distributed vectors (lane l owns dimensions l, l+32, ...) used by the one-warp-per-chain kernels.
+// Warp-distributed vectors used by the one-warp-per-chain kernels: register i of lane l holds dimension
+// hmc_dim<NJ>(l, i).  NJ % 4 == 0: blocks of 4 adjacent dimensions per lane (128-bit shared/global accesses, one
+// Philox call per block); NJ < 4 (D <= 32): strided, so that small D still spreads over the lanes.
 // ---------------------------------------------------------------------------------------------------------
-// y = M x for a D x D matrix given by its transpose Mt[k][j] (row pitch Dp); x, y distributed over the warp
-// (lane l owns j = l, l+32, ...).  x is staged in a per-warp shared buffer and read back as a broadcast.
-template <typename T, int NJ>
+template <int NJ>
+__device__ __forceinline__ int hmc_dim(int lane, int i) {
+    if constexpr (NJ % 4 == 0) return (i >> 2) * 128 + 4 * lane + (i & 3);
+    else return lane + 32 * i;
+}
+
+__device__ __forceinline__ void hmc_load4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void hmc_load4(const double* p, double (&v)[4]) {
+    const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
+
+// explicit shared-space loads (the matrix pointer is chosen at run time, so the compiler would otherwise emit
+// generic-address LD.E instead of LDS)
+__device__ __forceinline__ void hmc_lds4(uint32_t addr, float (&v)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void hmc_lds4(uint32_t addr, double (&v)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(addr + 16));
+}
+
+// y = M x for a D x D matrix given by its transpose Mt[k][j] (row pitch Dp, a multiple of 4, columns >= D zero);
+// x, y distributed over the warp.  x is staged in a per-warp shared buffer (Dp entries) and read back as a
+// broadcast, four k at a time.  SM = the matrix sits in shared memory with Dp zero-padded ROWS as well, so the
+// k loop needs no bounds checks.
+template <typename T, int NJ, bool SM>
 __device__ __forceinline__ void matvec_t(const T* __restrict__ Mt, int D, int Dp, const T (&x)[NJ], T (&y)[NJ],
                                          int lane, T* __restrict__ xs) {
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) { y[i] = T(0); const int j = lane + 32 * i; if (j < D) xs[j] = x[i]; }
+    for (int i = 0; i < NJ; ++i) { y[i] = T(0); const int j = hmc_dim<NJ>(lane, i); if (j < Dp) xs[j] = (j < D) ? x[i] : T(0); }
     __syncwarp();
+    if constexpr (NJ % 4 == 0 && SM) {
+        const uint32_t xs_a = (uint32_t)__cvta_generic_to_shared(xs);
+        const uint32_t m_a = (uint32_t)__cvta_generic_to_shared(Mt) + (uint32_t)(4 * lane * sizeof(T));
+        const uint32_t pitch = (uint32_t)(Dp * sizeof(T));
+        const bool on = 4 * lane < Dp;
 #pragma unroll 2
-    for (int k = 0; k < D; ++k) {
-        const T xk = xs[k];
-        const T* row = Mt + (size_t)k * Dp;
+        for (int kb = 0; kb < Dp; kb += 4) {
+            T xk[4];
+            hmc_lds4(xs_a + (uint32_t)(kb * sizeof(T)), xk);
 #pragma unroll
-        for (int i2 = 0; i2 < NJ; ++i2) {
-            const int j = lane + 32 * i2;
-            if (j < D) y[i2] = fma(row[j], xk, y[i2]);
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int i4 = 0; i4 < NJ / 4; ++i4) {
+                    if (i4 == 0 ? on : (i4 * 128 + 4 * lane < Dp)) {
+                        T v[4];
+                        hmc_lds4(m_a + (uint32_t)(kb + kk) * pitch + (uint32_t)(i4 * 128 * sizeof(T)), v);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) y[4 * i4 + c] = fma(v[c], xk[kk], y[4 * i4 + c]);
+                    }
+                }
+            }
+        }
+    } else if constexpr (NJ % 4 == 0) {
+        for (int kb = 0; kb < D; kb += 4) {
+            T xk[4];
+            hmc_load4(xs + kb, xk);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kb + kk < D) {
+                    const T* row = Mt + (size_t)(kb + kk) * Dp;
+#pragma unroll
+                    for (int i4 = 0; i4 < NJ / 4; ++i4) {
+                        const int j0 = i4 * 128 + 4 * lane;
+                        if (j0 < Dp) {
+                            T v[4];
+                            hmc_load4(row + j0, v);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) y[4 * i4 + c] = fma(v[c], xk[kk], y[4 * i4 + c]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int k = 0; k < D; ++k) {
+            const T xk = xs[k];
+            const T* row = Mt + (size_t)k * Dp;
+#pragma unroll
+            for (int i2 = 0; i2 < NJ; ++i2) {
+                const int j = hmc_dim<NJ>(lane, i2);
+                if (j < D) y[i2] = fma(row[j], xk, y[i2]);
+            }
         }
     }
     __syncwarp();

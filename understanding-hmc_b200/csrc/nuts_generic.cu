@@ -21,16 +21,18 @@ namespace {
 
 enum { HMC_STREAM_NUTS_INNER = 3 };
 
-template <typename T, int NJ>
-__global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, int smem_mask) {
+template <typename T, int NJ, bool SM>
+__global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.target.D, Dp = a.target.D_pad;
     const T* Ft = (const T*)a.target.Ft;
     T* xs = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * Dp;
     {
         T* s = (T*)smem_raw + (size_t)(blockDim.x >> 5) * Dp;
-        const int n = D * Dp;
-        if (smem_mask & 1) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Ft[t]; Ft = s; }
+        if constexpr (SM) {      // Dp x Dp tile: the rows D..Dp-1 are zero so that the mat-vec needs no row checks
+            for (int t = threadIdx.x; t < Dp * Dp; t += blockDim.x) s[t] = (t < D * Dp) ? Ft[t] : T(0);
+            Ft = s;
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
@@ -49,28 +51,28 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
     T q[NJ], p[NJ], f[NJ], d[NJ], mu[NJ], dt[NJ], t1[NJ], t2[NJ];
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
-        const int j = lane + 32 * i;
+        const int j = hmc_dim<NJ>(lane, i);
         mu[i] = (j < D) ? mu_g[j] : T(0);
         dt[i] = (j < D) ? dt_g[j] : T(0);
         q[i] = T(0); p[i] = T(0); f[i] = T(0);
     }
     auto row_store = [&](int row, const T (&v)[NJ]) {
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) scr[(size_t)row * Dp + j] = v[i]; }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) scr[(size_t)row * Dp + j] = v[i]; }
     };
     auto row_load = [&](int row, T (&v)[NJ]) {
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; v[i] = (j < D) ? scr[(size_t)row * Dp + j] : T(0); }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); v[i] = (j < D) ? scr[(size_t)row * Dp + j] : T(0); }
     };
     auto draw_p = [&](int iter) {
         if (a.p_tape) {
             const double* src = a.p_tape + ((size_t)m * (a.Niter + 1) + iter) * D;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; p[i] = (j < D) ? (T)src[j] : T(0); }
+            for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); p[i] = (j < D) ? (T)src[j] : T(0); }
         } else {
 #pragma unroll
             for (int i = 0; i < NJ; ++i) {
-                const int j = lane + 32 * i;
+                const int j = hmc_dim<NJ>(lane, i);
                 if (j < D) {
                     float4 z = hmc_normal4(a.seed, gid, (uint32_t)iter, (uint32_t)(j >> 2));
                     const int r = j & 3;
@@ -82,10 +84,13 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
     auto force = [&]() {                      // f = P (q - mu)
 #pragma unroll
         for (int i = 0; i < NJ; ++i) d[i] = q[i] - mu[i];
-        matvec_t<T, NJ>(Ft, D, Dp, d, f, lane, xs);
+        matvec_t<T, NJ, SM>(Ft, D, Dp, d, f, lane, xs);
     };
-    auto energy = [&]() -> double {           // E(q, p) with d, f current (samplers.py:819-823)
-        return 0.5 * dot_warp<T, NJ>(d, f) + vconst + 0.5 * dot_warp<T, NJ>(p, p);
+    auto energy = [&]() -> double {           // E(q, p) with d, f current (samplers.py:819-823): one warp reduction
+        T s = T(0);
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) s = fma(d[i], f[i], fma(p[i], p[i], s));
+        return 0.5 * (double)warp_sum<T>(s) + vconst;
     };
     auto leap = [&]() {                       // one leapfrog step, f = force at q on entry and on exit (samplers.py:831-839)
 #pragma unroll
@@ -103,11 +108,19 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
         *u_biased = ((double)(r.y >> 8) + 0.5) * 5.9604644775390625e-08;
         return (int)(r.x >> 31);
     };
+    Philox4 u_cache; u_cache.x = u_cache.y = u_cache.z = u_cache.w = 0u;
+    uint32_t u_cache_slot = 0xffffffffu;
     auto draw_u_inner = [&](int iter, int depth, int k) -> double {
         if (a.u_tape) return a.u_tape[(size_t)m * a.tape_u_stride + n_u++];
-        const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)iter, (uint32_t)((1u << depth) + (uint32_t)k),
-                                        HMC_STREAM_NUTS_INNER | ((uint32_t)(gid >> 32) << 8), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        return ((double)(r.x >> 8) + 0.5) * 5.9604644775390625e-08;
+        // step k of the sub-trajectory of depth d uses word (k & 3) of Philox counter ((1 << d) + k) >> 2
+        const uint32_t slot = ((uint32_t)iter << 22) ^ (((1u << depth) + (uint32_t)k) >> 2);
+        if (slot != u_cache_slot) {
+            u_cache = philox4x32_10((uint32_t)gid, (uint32_t)iter, ((1u << depth) + (uint32_t)k) >> 2,
+                                    HMC_STREAM_NUTS_INNER | ((uint32_t)(gid >> 32) << 8), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            u_cache_slot = slot;
+        }
+        const uint32_t w = (k & 3) == 0 ? u_cache.x : (k & 3) == 1 ? u_cache.y : (k & 3) == 2 ? u_cache.z : u_cache.w;
+        return ((double)(w >> 8) + 0.5) * 5.9604644775390625e-08;
     };
 
     double E_previous;
@@ -115,7 +128,7 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
     if (a.iter_begin == 0) {                                            // samplers.py:548-555
         const T* qs = (const T*)a.q_start + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
         draw_p(0);
         force();
         const double E0 = energy();
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
     } else {
         const T* qs = (const T*)a.state_q + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) q[i] = qs[j]; }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) q[i] = qs[j]; }
         E_previous = a.state_eprev[m];
         if (a.dir_tape) { n_dir = (long)cursors[0]; n_u = (long)cursors[1]; }   // resume the injected streams
     }
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
                         T s_cur = T(0), s_chk = T(0);                   // (q - q_check).p  and  (q - q_check).p_check
 #pragma unroll
                         for (int i = 0; i < NJ; ++i) { const T dq = q[i] - t1[i]; s_cur = fma(dq, p[i], s_cur); s_chk = fma(dq, t2[i], s_chk); }
-                        const double a_cur = warp_sum<double>((double)s_cur), a_chk = warp_sum<double>((double)s_chk);
+                        const T a_cur = warp_sum<T>(s_cur), a_chk = warp_sum<T>(s_chk);
                         // forward : Dq = q - q_chk, right_p = p, left_p = -p_chk   -> (Dq.p < 0) and (Dq.p_chk < 0)
                         // backward: Dq = q_chk - q, right_p = -p_chk, left_p = p   -> (Dq.(-p_chk) < 0) and (-Dq.p < 0)
                         //           i.e. ((q - q_chk).p_chk < 0) and ((q - q_chk).p < 0): the same two signs.
@@ -206,10 +219,14 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
                     if (reject) break;
                 }
                 // uniform progressive sampling inside the new sub-trajectory (samplers.py:743-751)
+                // numerator = exp(E_max - E_tmp) and the rescaling exp(E_max - E_max_previous): one of the two
+                // exponents is exactly 0, so a single exp() gives both factors
                 const double E_prev_max = E_max_new_now;
                 E_max_new_now = fmax(E_prev_max, E_tmp);
-                const double numer = exp(-(E_tmp - E_max_new_now));
-                pi_new = numer + exp(E_max_new_now - E_prev_max) * pi_new;
+                const double ex = exp(fabs(E_tmp - E_prev_max));
+                const bool new_max = E_tmp > E_prev_max;
+                const double numer = new_max ? 1.0 : ex;
+                pi_new = numer + (new_max ? ex : 1.0) * pi_new;
                 const double r = numer / pi_new;
                 const double u = draw_u_inner(it, depth, k);
                 if (u < r) row_store(R + 0, q);
@@ -238,8 +255,8 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
 #pragma unroll
                 for (int i = 0; i < NJ; ++i) { const T dq = t2[i] - t1[i]; s_r = fma(dq, rp[i], s_r); s_l = fma(-dq, lp[i], s_l); }
             }
-            right_term = warp_sum<double>((double)s_r) < 0;
-            left_term = warp_sum<double>((double)s_l) < 0;
+            right_term = warp_sum<T>(s_r) < T(0);
+            left_term = warp_sum<T>(s_l) < T(0);
             depth += 1;                                                 // samplers.py:784
         }
         __syncwarp();
@@ -248,13 +265,13 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a, 
         if (keep) {                                                     // samplers.py:790-791
             T* dst = q_chain + ((size_t)m * Lc + idx) * D;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) dst[j] = q[i]; }
+            for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) dst[j] = q[i]; }
         }
     }
     {
         T* qs = (T*)a.state_q + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) qs[j] = q[i]; }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) qs[j] = q[i]; }
         if (lane == 0) {
             a.state_eprev[m] = E_previous;
             cursors[0] = n_dir; cursors[1] = n_u;
@@ -272,12 +289,19 @@ int launch_nuts(const hmc_nuts_args& a, cudaStream_t stream) {
     const int warps = 4;
     const int blocks = (a.Nchain + warps - 1) / warps;
     const size_t mat = (size_t)a.target.D * a.target.D_pad * sizeof(T);
-    int mask = 0;
     size_t smem = (size_t)warps * a.target.D_pad * sizeof(T);
-    if (smem + mat <= 200 * 1024) { mask |= 1; smem += mat; }
-    auto kern = hmc_nuts_generic_kernel<T, NJ>;
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, warps * 32, smem, stream>>>(a, mask);
+    const size_t matp = (size_t)a.target.D_pad * a.target.D_pad * sizeof(T);
+    (void)mat;
+    if (smem + matp <= 200 * 1024) {
+        smem += matp;
+        auto kern = hmc_nuts_generic_kernel<T, NJ, true>;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, warps * 32, smem, stream>>>(a);
+    } else {
+        auto kern = hmc_nuts_generic_kernel<T, NJ, false>;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, warps * 32, smem, stream>>>(a);
+    }
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }

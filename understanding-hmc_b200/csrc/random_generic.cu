@@ -7,7 +7,7 @@
 
 namespace {
 
-template <typename T, int NJ>
+template <typename T, int NJ, bool SM>
 __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args a, int smem_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.target.D, Dp = a.target.D_pad;
@@ -19,7 +19,10 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     {   // stage the matrices that fit into shared memory (decided by the host)
         T* s = (T*)smem_raw + (size_t)(blockDim.x >> 5) * Dp;
         const int n = D * Dp;
-        if (smem_mask & 1) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Ft[t]; Ft = s; s += n; }
+        if constexpr (SM) {      // identity metric, F fits: Dp x Dp tile with zero rows D..Dp-1 (no row checks in the mat-vec)
+            for (int t = threadIdx.x; t < Dp * Dp; t += blockDim.x) s[t] = (t < n) ? Ft[t] : T(0);
+            Ft = s;
+        } else if (smem_mask & 1) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Ft[t]; Ft = s; s += n; }
         if ((smem_mask & 2) && Pt) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Pt[t]; Pt = s; s += n; }
         if ((smem_mask & 4) && Mit) { for (int t = threadIdx.x; t < n; t += blockDim.x) s[t] = Mit[t]; Mit = s; s += n; }
         __syncthreads();
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     T q[NJ], p[NJ], f[NJ], d[NJ], mu[NJ], dt[NJ], tmp[NJ];
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
-        const int j = lane + 32 * i;
+        const int j = hmc_dim<NJ>(lane, i);
         mu[i] = (j < D) ? mu_g[j] : T(0);
         dt[i] = (j < D) ? dt_g[j] : T(0);
         q[i] = T(0); p[i] = T(0); f[i] = T(0);
@@ -46,11 +49,11 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
         if (a.p_tape) {
             const double* src = a.p_tape + ((size_t)m * (a.Niter + 1) + iter) * D;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; p[i] = (j < D) ? (T)src[j] : T(0); }
+            for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); p[i] = (j < D) ? (T)src[j] : T(0); }
         } else {
 #pragma unroll
             for (int i = 0; i < NJ; ++i) {
-                const int j = lane + 32 * i;
+                const int j = hmc_dim<NJ>(lane, i);
                 if (j < D) {
                     float4 z = hmc_normal4(a.seed, gid, (uint32_t)iter, (uint32_t)(j >> 2));
                     const int r = j & 3;
@@ -60,21 +63,21 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
             if (Lct) {   // p = Lc z ~ N(0, cov_p)   (samplers.py:829)
 #pragma unroll
                 for (int i = 0; i < NJ; ++i) tmp[i] = p[i];
-                matvec_t<T, NJ>(Lct, D, Dp, tmp, p, lane, xs);
+                matvec_t<T, NJ, false>(Lct, D, Dp, tmp, p, lane, xs);
             }
         }
     };
     auto force = [&]() {          // f = F (q - mu)
 #pragma unroll
         for (int i = 0; i < NJ; ++i) d[i] = q[i] - mu[i];
-        matvec_t<T, NJ>(Ft, D, Dp, d, f, lane, xs);
+        matvec_t<T, NJ, SM>(Ft, D, Dp, d, f, lane, xs);
     };
     auto potential = [&]() -> double {   // V(q); requires d, f current for q
-        if (Pt) { matvec_t<T, NJ>(Pt, D, Dp, d, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(d, tmp) + a.target.v_const; }
+        if (Pt) { matvec_t<T, NJ, false>(Pt, D, Dp, d, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(d, tmp) + a.target.v_const; }
         return 0.5 * dot_warp<T, NJ>(d, f) + a.target.v_const;
     };
     auto kinetic = [&]() -> double {
-        if (Mit) { matvec_t<T, NJ>(Mit, D, Dp, p, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(p, tmp); }
+        if (Mit) { matvec_t<T, NJ, false>(Mit, D, Dp, p, tmp, lane, xs); return 0.5 * dot_warp<T, NJ>(p, tmp); }
         return 0.5 * dot_warp<T, NJ>(p, p);
     };
 
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     if (a.iter_begin == 0) {                                            // samplers.py:413-420
         const T* qs = (const T*)a.q_start + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
         draw_p(0);
         force();
         const double E0 = potential() + kinetic();
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     } else {
         const T* qs = (const T*)a.state_q + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) q[i] = qs[j]; }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) q[i] = qs[j]; }
         E_previous = a.state_eprev[m];
     }
 
@@ -116,7 +119,11 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
         sumL += L; sumL2 += (unsigned long long)L * L;
         const bool trace = a.phi_q && gid == 0 && it <= a.N_save_chain0;
         double* phi = trace ? a.phi_q + (size_t)(it - 1) * a.L_high * 2 : nullptr;
-        if (trace) { if (lane < 2 && lane < D) phi[lane] = (double)q[0]; if (lane == 0) a.phi_len[it - 1] = L + 1; }
+        auto trace_row = [&](int row) {       // first two coordinates of the current position (samplers.py:445, 452)
+            if constexpr (NJ % 4 == 0) { if (lane == 0) { phi[2 * row] = (double)q[0]; if (D > 1) phi[2 * row + 1] = (double)q[1]; } }
+            else { if (lane < 2 && lane < D) phi[2 * row + lane] = (double)q[0]; }
+        };
+        if (trace) { trace_row(0); if (lane == 0) a.phi_len[it - 1] = L + 1; }
         for (int l = 1; l <= L; ++l) {                                  // samplers.py:448-452, leap_frog :831-839
 #pragma unroll
             for (int i = 0; i < NJ; ++i) {
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
             force();
 #pragma unroll
             for (int i = 0; i < NJ; ++i) p[i] = p[i] - dt[i] * f[i] / T(2);
-            if (trace && lane < 2 && lane < D) phi[2 * l + lane] = (double)q[0];
+            if (trace) trace_row(l);
         }
         const double E_final = potential() + kinetic();                 // samplers.py:455
         const double dE = E_final - E_initial;
@@ -144,13 +151,13 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
         if (keep) {                                                     // samplers.py:465-471 (Q4: negative-index writes skipped)
             T* dst = q_chain + ((size_t)m * Lc + idx) * D;
 #pragma unroll
-            for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) dst[j] = q[i]; }
+            for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) dst[j] = q[i]; }
         }
     }
     {
         T* qs = (T*)a.state_q + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = lane + 32 * i; if (j < D) qs[j] = q[i]; }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) qs[j] = q[i]; }
         if (lane == 0) {
             a.state_eprev[m] = E_previous;
             if (a.counters) {
@@ -174,9 +181,17 @@ int launch_generic(const hmc_random_args& a, cudaStream_t stream) {
     if (smem + mat <= budget) { mask |= 1; smem += mat; }
     if (a.target.Pt && smem + mat <= budget) { mask |= 2; smem += mat; }
     if (a.target.Mit && smem + mat <= budget) { mask |= 4; smem += mat; }
-    auto kern = hmc_random_generic_kernel<T, NJ>;
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, warps * 32, smem, stream>>>(a, mask);
+    const size_t matp = (size_t)a.target.D_pad * a.target.D_pad * sizeof(T);
+    const size_t smem_sm = (size_t)warps * a.target.D_pad * sizeof(T) + matp;
+    if (!a.target.Pt && !a.target.Mit && !a.target.Lct && smem_sm <= budget) {
+        auto kern = hmc_random_generic_kernel<T, NJ, true>;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sm));
+        kern<<<blocks, warps * 32, smem_sm, stream>>>(a, 0);
+    } else {
+        auto kern = hmc_random_generic_kernel<T, NJ, false>;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, warps * 32, smem, stream>>>(a, mask);
+    }
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }
