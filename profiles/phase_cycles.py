@@ -34,3 +34,23 @@ for variant in (1, 2, 3, 0):
              v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps))
     print("   inside service, cycles per warp-step: move/store/refill %.0f, gen_momentum %.0f, rest (bookkeeping + register refresh) %.0f"
           % (v[6] / steps, v[7] / steps, (v[0] - v[6] - v[7]) / steps))
+
+# ---- tensor-core kernel ----
+lib.hmc_debug_tc_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+os.environ["HMC_B200_TILE_VARIANT"] = "0"
+H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB * 2, sampler_type="Random", dt=0.1, L_low=5, L_high=20,
+                  dtype="float32", kernel="tc", seed=1, target=spec)
+run = H.prepare_random(q0)
+run["args"].iter_begin, run["args"].iter_end = 0, IB
+L.check(lib.hmc_random_run(run["args"], L.current_stream_ptr())); torch.cuda.synchronize()
+lib.hmc_debug_tc_cycles(None, 1)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+run["args"].iter_begin, run["args"].iter_end = IB, 2 * IB
+L.check(lib.hmc_random_run(run["args"], L.current_stream_ptr()))
+e1.record(); torch.cuda.synchronize()
+out = (C.c_ulonglong * 8)()
+lib.hmc_debug_tc_cycles(out, 0)
+v = np.array(list(out), dtype=float); steps = v[5]
+print("tensor-core kernel (128 chains/CTA, thread per chain): %.2f ms; warp-passes %d; cycles per pass: chain/momentum service %.0f, split+store positions %.0f, sync+MMA+wait %.0f, TMEM read + leapfrog update %.0f, bookkeeping %.0f"
+      % (e0.elapsed_time(e1), steps, v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps))

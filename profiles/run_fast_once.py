@@ -9,7 +9,7 @@ D, Nc, IB, NL = 100, int(sys.argv[1]) if len(sys.argv) > 1 else 28416, int(sys.a
 spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
 q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
 H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB * NL, sampler_type="Random", dt=0.1, L_low=5, L_high=20,
-                  dtype="float32", kernel="fast", seed=1, target=spec)
+                  dtype="float32", kernel=os.environ.get("HMC_B200_KERNEL", "fast"), seed=1, target=spec)
 run = H.prepare_random(q0)
 lib = L.load()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(NL + 1)]

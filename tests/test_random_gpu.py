@@ -70,11 +70,11 @@ def _teacher_forced(fx, dtype, kernel, always_accept):
 FAST_OK = ("random_case3c_small", "random_case2c_small")     # the FFMA2 kernel covers 40 < D <= 100
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
 @pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small", "random_case2c_small"])
 def test_f32_teacher_forced_trajectories(name, kernel):
-    if kernel == "fast" and name not in FAST_OK:
-        pytest.skip("fast kernel covers 40 < D <= 100")
+    if kernel in ("fast", "tc") and name not in FAST_OK:
+        pytest.skip("fused kernels: fast covers 20 < D <= 128, tc covers D = 100")
     fx = load(name)
     R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=True)
     D = int(fx["D"])
@@ -90,11 +90,11 @@ def test_f32_teacher_forced_trajectories(name, kernel):
     np.testing.assert_allclose(H.E_chain[:, 1, 0], E_want, rtol=3e-5, atol=3e-5)
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
 @pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small"])
 def test_f32_teacher_forced_decisions(name, kernel):
-    if kernel == "fast" and name not in FAST_OK:
-        pytest.skip("fast kernel covers 40 < D <= 100")
+    if kernel in ("fast", "tc") and name not in FAST_OK:
+        pytest.skip("fused kernels: fast covers 20 < D <= 128, tc covers D = 100")
     fx = load(name)
     R, H, B = _teacher_forced(fx, "float32", kernel, always_accept=False)
     D = int(fx["D"])
@@ -220,7 +220,8 @@ def test_target_extraction_and_errors():
     assert ei.value.code == L.HMC_E_BADARG
 
 
-def test_fast_kernel_slot_refill_matches_generic():
+@pytest.mark.parametrize("kernel", ["fast", "tc"])
+def test_fast_kernel_slot_refill_matches_generic(kernel):
     """More chains than resident slots (148 SMs x 192): finished slots pull new chains from the queue, over
     several iteration-block launches.  Same Philox draws as the generic kernel => same streams up to float32
     summation order (first trajectory rel 1e-5, acceptance within 0.2 %)."""
@@ -230,7 +231,7 @@ def test_fast_kernel_slot_refill_matches_generic():
     q_start = np.random.RandomState(5).standard_normal((Nchain, D)).astype(np.float32) * 1.4
     kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=0.1, L_low=5,
               L_high=20, dtype="float32", seed=11, target=spec)
-    F = S.HMC_sampler(D, None, None, kernel="fast", iter_block=3, **kw)
+    F = S.HMC_sampler(D, None, None, kernel=kernel, iter_block=3, **kw)
     F.gen_sample(q_start, verbose=False, quiet=True)
     G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
     G.gen_sample(q_start, verbose=False, quiet=True)

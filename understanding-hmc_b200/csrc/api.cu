@@ -16,6 +16,8 @@ void hmc_set_error(const char* fmt, ...) {
 int hmc_random_run_generic(const hmc_random_args& a, cudaStream_t stream);
 int hmc_random_run_fast(const hmc_random_args& a, cudaStream_t stream);
 bool hmc_random_fast_supported(const hmc_random_args& a, const char** why);
+int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream);
+bool hmc_random_tc_supported(const hmc_random_args& a, const char** why);
 int hmc_nuts_run_generic(const hmc_nuts_args& a, cudaStream_t stream);
 
 extern "C" int hmc_version(void) { return HMC_B200_VERSION; }
@@ -62,6 +64,13 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
             return HMC_E_UNSUPPORTED;
         }
         return hmc_random_run_fast(a, stream);
+    }
+    if (kernel == HMC_KERNEL_TC) {
+        if (!hmc_random_tc_supported(a, &why)) {
+            hmc_set_error("tensor-core kernel does not cover this configuration: %s", why);
+            return HMC_E_UNSUPPORTED;
+        }
+        return hmc_random_run_tc(a, stream);
     }
     if (kernel == HMC_KERNEL_GENERIC) return hmc_random_run_generic(a, stream);
     hmc_set_error("unknown kernel id %d", a.kernel);

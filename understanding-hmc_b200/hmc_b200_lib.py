@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhmc_b200.so")
 
 HMC_F32, HMC_F64 = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
-KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST}
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC = 0, 1, 2, 3
+KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST, "tc": KERNEL_TC}
 HMC_OK, HMC_E_BADARG, HMC_E_UNSUPPORTED, HMC_E_CUDA, HMC_E_DMAX = 0, 1, 2, 3, 4
 
 EXPORTS = ["hmc_random_run", "hmc_nuts_run", "hmc_diag_moments", "hmc_diag_variogram", "hmc_philox_draws",

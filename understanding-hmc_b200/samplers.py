@@ -7,7 +7,7 @@ diagnostics (utils.py:77-179) run in libhmc_b200.so through the C-ABI of include
 fallback: a target that is not a multivariate normal, or a missing CUDA library, raises.
 
 Extra keyword-only constructor arguments (defaults keep the reference behaviour):
-  dtype="float32"|"float64", seed=0 (Philox key), kernel="auto"|"generic"|"fast", draws=None (the reference's
+  dtype="float32"|"float64", seed=0 (Philox key), kernel="auto"|"generic"|"fast"|"tc", draws=None (the reference's
   own draws as structured tapes, see tests/golden/make_golden.py), on_dmax="assert"|"stop" (NUTS),
   chain_id0=0 / distributed=False (chains sharded over ranks; counters and moments are all-reduced),
   iter_block=None (iterations per kernel launch), target=None (explicit ``MVNSpec`` instead of probing V/dVdq).
