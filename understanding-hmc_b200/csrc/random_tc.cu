@@ -2,22 +2,25 @@
 //
 // Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839).
 //
-// One CTA = 128 chains = 128 threads; THREAD t OWNS CHAIN t: its shifted position d = q - mu and its momentum p
-// live in that thread's registers, so every per-chain quantity (energies, Metropolis accept, trajectory length,
-// bookkeeping) is thread-local -- no cross-lane reductions.  The gradient of all 128 chains,
+// One CTA = 128 chains, 512 threads.  The gradient of all 128 chains,
 //       G[128 x N] = Dm[128 x K] * F[N x K]^T          (K = N = 112: D = 100 zero-padded to a multiple of 16)
-// runs on the 5th-generation tensor cores: the positions are written to shared memory as three bf16 parts
-// (d = d1 + d2 + d3 exactly), the force matrix is split once the same way, and six tcgen05.mma passes
-// (1,3) (3,1) (2,2) (1,2) (2,1) (1,1) accumulate in fp32 in tensor memory -- the dropped terms are O(2^-24).  The
-// accumulator row of chain t is TMEM lane t, read back with tcgen05.ld by thread t (the "32x32b" shape).
+// runs on the 5th-generation tensor cores: the shifted positions d = q - mu are kept in shared memory as three bf16
+// parts (d = d1 + d2 + d3 exactly), the force matrix is split once the same way, and six tcgen05.mma passes
+// (1,3) (3,1) (2,2) (1,2) (2,1) (1,1) accumulate in fp32 in tensor memory -- the dropped terms are O(2^-24).
 // Shared-memory operands use the canonical no-swizzle K-major layout: 16-byte chunk (kc, row) at (kc*rows + row)*16
-// (LBO = rows*16 between K chunks, SBO = 128 between 8-row groups), which makes the per-thread row writes
-// conflict-free 128-bit stores.
+// (LBO = rows*16 between K chunks, SBO = 128 between 8-row groups), so per-thread row writes are conflict-free
+// 128-bit stores.
 //
-// Every chain advances one gradient evaluation per pass; iteration boundaries are per-thread events:
-// the first point of each trajectory is a gradient-only pass (E_initial, first half kick), so an iteration costs
-// L + 1 evaluations.  Momentum refresh is warp-cooperative (one Philox call per lane, same draws as every other
-// kernel); finished chains pull the next chain from a global queue.
+// The accumulator row of chain c is TMEM lane c.  FOUR threads share a chain: thread (warp w, lane) works on chain
+// 32*(w%4) + lane (the TMEM lanes a warp may read) and on the dimension slice w/4 (24, 24, 24, 28 dims): it reads
+// its slice of the gradient with tcgen05.ld, keeps the momentum slice in registers, updates the position slice
+// (fp32 copy in shared memory) and re-splits it.  Per-chain sums (d.g, p.p) are combined through shared memory by
+// the slice-0 thread, which does the chain's bookkeeping (energies, Metropolis accept on a Philox uniform, new
+// trajectory length) and posts a command that all four slice threads apply (sample store, restore, momentum
+// refresh).  Every chain advances one gradient evaluation per pass; iteration boundaries are per-chain events
+// (SURVEY H3); the first point of each trajectory is a gradient-only pass, so an iteration costs L + 1
+// evaluations.  Momentum refresh is warp-cooperative (one Philox call per lane, same draws as every other kernel);
+// finished chains pull the next chain from a global queue.
 #include "hmc_common.cuh"
 #include <cuda_bf16.h>
 
@@ -34,10 +37,17 @@ namespace {
 
 constexpr int TC_ND = 100;          // dimensions handled by this instantiation
 constexpr int TC_KP = 112;          // padded K = N (multiple of 16)
-constexpr int TC_KC = TC_KP / 8;    // 16-byte chunks (8 bf16) per row
+constexpr int TC_KC = TC_KP / 8;    // 16-byte chunks (8 bf16) per operand row
 constexpr int TC_M = 128;           // chains per CTA
+constexpr int TC_SPL = 4;           // threads (dimension slices) per chain
+constexpr int TC_THREADS = TC_M * TC_SPL;
 constexpr int TC_APART = TC_KC * TC_M * 16;     // bytes of one A part
 constexpr int TC_BPART = TC_KC * TC_KP * 16;    // bytes of one B part
+constexpr int TC_DCH = TC_ND / 4;               // fp32 position chunks (4 dims) per chain
+constexpr int TC_SLOTS = 5;                     // momentum staging slots per 32-chain group and round
+
+enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_REFRESH = 32, CMD_INIT0 = 64 };
+enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -50,7 +60,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// x = b1 + b2 + b3 exactly (three bf16 parts); returns the parts of two values packed as bf16x2 (lo = x0, hi = x1)
+// x = b1 + b2 + b3 exactly (three bf16 parts); the parts of two values packed as bf16x2 (lo = x0, hi = x1)
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
     __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1);
     h1 = *reinterpret_cast<uint32_t*>(&a);
@@ -110,25 +120,43 @@ __device__ __noinline__ void tc_gen(const TcGen g, long m, uint64_t gid, int ite
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(TC_M, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
+struct TcShared {                       // small per-chain arrays in shared memory
+    float2 red[TC_SPL][TC_M];           // partial (d.g, p.p) per slice
+    int mode[TC_M];                     // MODE_* of the gradient being evaluated
+    int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread
+    int cm[TC_M];                       // local chain index the command refers to (row addressing)
+    int cidx[TC_M];                     // stored-sample index of the command
+    int cit[TC_M];                      // iteration whose momentum is to be drawn
+    float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
+    int gL[TC_M];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* Ap = smem;                                   // 3 parts [KC][128] 16-byte chunks
     unsigned char* Bp = Ap + 3 * TC_APART;                      // 3 parts [KC][112]
-    float* mu_s = reinterpret_cast<float*>(Bp + 3 * TC_BPART);  // [KP]
+    float4* Df = reinterpret_cast<float4*>(Bp + 3 * TC_BPART);  // fp32 positions [TC_DCH][128] 16-byte chunks
+    float* mu_s = reinterpret_cast<float*>(Df + TC_DCH * TC_M); // [KP]
     float* dt_s = mu_s + KP;                                    // [KP]
-    float* stage_all = dt_s + KP;                               // [4 warps][128] momentum staging
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_all + 4 * 128);
+    float* stage_all = dt_s + KP;                               // [4 groups][TC_SLOTS][128] momentum staging
+    TcShared* sh = reinterpret_cast<TcShared*>(stage_all + 4 * TC_SLOTS * 128);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sh + 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float* stage = stage_all + warp * 128;
+    const int grp = warp & 3;                    // 32-chain group == TMEM lane quarter this warp may access
+    const int slice = warp >> 2;                 // dimension slice
+    const int chain = grp * 32 + lane;           // chain slot of this thread
+    const int j0 = 24 * slice;                   // first dimension of the slice
+    const bool wide = slice == TC_SPL - 1;       // the last slice has 28 dims, the others 24
 
-    // ---- one-time set-up: zero A (padding chunks stay zero), split the force matrix into bf16 parts ------------
-    for (int t = tid; t < 3 * TC_APART / 16; t += TC_M) reinterpret_cast<uint4*>(Ap)[t] = make_uint4(0u, 0u, 0u, 0u);
+    // ---- one-time set-up ---------------------------------------------------------------------------------------------
+    for (int t = tid; t < 3 * TC_APART / 16; t += TC_THREADS) reinterpret_cast<uint4*>(Ap)[t] = make_uint4(0u, 0u, 0u, 0u);
+    for (int t = tid; t < TC_DCH * TC_M; t += TC_THREADS) Df[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         const float* Ft = (const float*)a.target.Ft;            // Ft[k][n] = F[n][k]; B row n holds F[n][.] (K-major)
         const int Dpad = a.target.D_pad;
-        for (int t = tid; t < KC * KP; t += TC_M) {             // one 16-byte chunk (8 k values) of row n per item
+        for (int t = tid; t < KC * KP; t += TC_THREADS) {       // one 16-byte chunk (8 k values) of row n per item
             const int kc = t / KP, n = t % KP;
             uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
@@ -142,10 +170,11 @@ __global__ void __launch_bounds__(TC_M, 1) hmc_random_tc_kernel(const hmc_random
             reinterpret_cast<uint4*>(Bp + TC_BPART)[t] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
             reinterpret_cast<uint4*>(Bp + 2 * TC_BPART)[t] = make_uint4(w3[0], w3[1], w3[2], w3[3]);
         }
-        for (int t = tid; t < KP; t += TC_M) {
+        for (int t = tid; t < KP; t += TC_THREADS) {
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
+        for (int t = tid; t < TC_M; t += TC_THREADS) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; }
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -159,126 +188,330 @@ __global__ void __launch_bounds__(TC_M, 1) hmc_random_tc_kernel(const hmc_random
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem + ((uint32_t)(grp * 32) << 16) + (uint32_t)j0;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
     float* q_chain = (float*)a.q_chain;
     float* q0g = (float*)a.state_q;
     const double vconst = a.target.v_const;
-    const float dt0 = dt_s[0];
-    const bool udt = (a.flags & 1) != 0;
     TcGen ga;
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
     ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
 
-    // ---- per-thread chain state ------------------------------------------------------------------------------------
-    float d[D], p[D];
+    // ---- per-thread state -----------------------------------------------------------------------------------------------
+    float p[28];                     // momentum slice (registers)
 #pragma unroll
-    for (int j = 0; j < D; ++j) { d[j] = 0.f; p[j] = 0.f; }
+    for (int j = 0; j < 28; ++j) p[j] = 0.f;
+    // bookkeeping state of chain `chain`, used by the slice-0 thread only
     long m = -1;                     // local chain index, -1 = no chain
     int it = 0, l = 0, L = 1;        // iteration, point index of the next gradient, trajectory length
     bool init = false;               // chain start: E_chain[.,0] still to be recorded
-    bool want = true;                // needs a (new) chain
-    bool refresh = false;            // needs the momentum of iteration `it`
+    bool want = (slice == 0);        // needs a (new) chain
+    bool fetch = false;              // momentum of iteration `it` was requested, results are in sh->g*
     double E_init = 0.0, E_prev = 0.0;
     float K0 = 0.f, Knew = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
     uint32_t phase = 0;
+    bool have_grad = false;          // a gradient pass has been issued and its accumulator is to be consumed
 #ifdef HMC_PROFILE_PHASES
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
+    // position slice helpers -------------------------------------------------------------------------------------------------
+    // write the slice [j0, j0+nj) of the fp32 row and re-split it into the three bf16 parts (8-dim operand chunks)
+    auto store_slice = [&](const float (&x)[32], int nch4) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c)
+            if (c < nch4) Df[(j0 / 4 + c) * TC_M + chain] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            if (kc < 3 || wide) {
+                uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split3(x[8 * kc + 2 * e], x[8 * kc + 2 * e + 1], w1[e], w2[e], w3[e]);
+                const int off = ((j0 / 8 + kc) * TC_M + chain) * 16;
+                *reinterpret_cast<uint4*>(Ap + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                *reinterpret_cast<uint4*>(Ap + TC_APART + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+                *reinterpret_cast<uint4*>(Ap + 2 * TC_APART + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+            }
+        }
+    };
+
     while (true) {
         TP_T(t0);
-        // ===== A. chains that need a new chain id / a new momentum (per-thread decisions, warp-cooperative draws) ===
-        if (want) {
-            want = false;
-            const unsigned int nxt = atomicAdd(queue, 1u);
-            if (nxt < (unsigned int)a.Nchain) {
-                m = (long)nxt;
-                it = a.iter_begin + 1;
-                const float* src = (a.iter_begin == 0) ? (const float*)a.q_start + (size_t)m * D : q0g + (size_t)m * D;
-#pragma unroll
-                for (int j4 = 0; j4 < D / 4; ++j4) {
-                    const float4 v = *reinterpret_cast<const float4*>(src + 4 * j4);
-                    d[4 * j4 + 0] = v.x - mu_s[4 * j4 + 0]; d[4 * j4 + 1] = v.y - mu_s[4 * j4 + 1];
-                    d[4 * j4 + 2] = v.z - mu_s[4 * j4 + 2]; d[4 * j4 + 3] = v.w - mu_s[4 * j4 + 3];
-                    if (a.iter_begin == 0) {
-                        *reinterpret_cast<float4*>(q0g + (size_t)m * D + 4 * j4) = v;
-                        *reinterpret_cast<float4*>(q_chain + (size_t)m * Lc * D + 4 * j4) = v;          // samplers.py:413
-                    }
+        // ===== P1. consume the gradient: thread-local leapfrog update of the slice (samplers.py:835-837) ==============
+        if (have_grad) {
+            {
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile("{\n\t.reg .pred pw;\n\tmbarrier.try_wait.parity.shared::cta.b64 pw, [%1], %2;\n\tselp.u32 %0, 1, 0, pw;\n\t}"
+                                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
                 }
-                init = (a.iter_begin == 0);
-                if (!init) E_prev = a.state_eprev[m];
-                if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
-                refresh = true;
-            } else {
-                m = -1;
-#pragma unroll
-                for (int j = 0; j < D; ++j) { d[j] = 0.f; p[j] = 0.f; }
+                phase ^= 1u;
             }
-        }
-        {
-            unsigned need = __ballot_sync(HMC_FULL_MASK, refresh);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const long m_s = __shfl_sync(HMC_FULL_MASK, m, src);
-                const int it_s = __shfl_sync(HMC_FULL_MASK, it, src);
-                const int init_s = __shfl_sync(HMC_FULL_MASK, (int)init, src);
-                const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
-                float ks, ln; int Lx;
-                if (init_s) {                                               // samplers.py:415: chain-start momentum, K only
-                    tc_gen(ga, m_s, gid, 0, lane, stage, &ks, &Lx, &ln);
-                    if (lane == src) K0 = 0.5f * ks;
-                    __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            TP_T(t1);
+            TP_ADD(0, t0, t1);
+            const int md = sh->mode[chain];
+            // point index of the gradient: first = half kick + drift, last = half kick only, interior = second half
+            // kick of step l + first half kick of step l+1, drift
+            const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -1.0f : -0.5f);
+            const float dwt = (md == MODE_FIRST || md == MODE_MID) ? 1.f : 0.f;
+            uint32_t gv[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7]),
+                           "=r"(gv[8]), "=r"(gv[9]), "=r"(gv[10]), "=r"(gv[11]), "=r"(gv[12]), "=r"(gv[13]), "=r"(gv[14]), "=r"(gv[15])
+                         : "r"(tmem_row));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(gv[16]), "=r"(gv[17]), "=r"(gv[18]), "=r"(gv[19]), "=r"(gv[20]), "=r"(gv[21]), "=r"(gv[22]), "=r"(gv[23]),
+                           "=r"(gv[24]), "=r"(gv[25]), "=r"(gv[26]), "=r"(gv[27]), "=r"(gv[28]), "=r"(gv[29]), "=r"(gv[30]), "=r"(gv[31])
+                         : "r"(tmem_row + 16u));
+            asm volatile("tcgen05.wait::ld.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");      // TMEM reads ordered before the next MMA
+            float x[32];
+            float hv = 0.f, hk = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const bool on = c < 6 || (wide && c < 7);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on) v = Df[(j0 / 4 + c) * TC_M + chain];
+                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+            if (slice == 0 && md == MODE_FIRST && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0) {
+                double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;      // row 0: the start point (samplers.py:445)
+                phi[0] = (double)(x[0] + mu_s[0]); phi[1] = (double)(x[1] + mu_s[1]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 28; ++jj) {
+                if (jj < 24 || wide) {
+                    const float gj = __uint_as_float(gv[jj]);
+                    const float dtj = dt_s[j0 + jj];
+                    hv = fmaf(x[jj], gj, hv);
+                    const float pn = fmaf(gj, kwt * dtj, p[jj]);
+                    hk = fmaf(pn, pn, hk);
+                    p[jj] = pn;
+                    x[jj] = fmaf(pn, dwt * dtj, x[jj]);
                 }
-                tc_gen(ga, m_s, gid, it_s, lane, stage, &ks, &Lx, &ln);     // samplers.py:431, 441, 461
-                if (lane == src) {
-#pragma unroll
-                    for (int j4 = 0; j4 < D / 4; ++j4) {
-                        const float4 v = *reinterpret_cast<const float4*>(stage + 4 * j4);
-                        p[4 * j4 + 0] = v.x; p[4 * j4 + 1] = v.y; p[4 * j4 + 2] = v.z; p[4 * j4 + 3] = v.w;
-                    }
-                    Knew = 0.5f * ks; L = Lx; lnu = ln; l = 0;
-                    n_sumL += (unsigned int)Lx; n_sumL2 += (unsigned int)(Lx * Lx);
-                    refresh = false;
-                    if (a.phi_q && a.chain_id0 + m == 0 && it <= a.N_save_chain0) {          // samplers.py:442-445
-                        double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;
-                        phi[0] = (double)(d[0] + mu_s[0]); phi[1] = (double)(d[1] + mu_s[1]);
-                        a.phi_len[it - 1] = Lx + 1;
-                    }
-                }
-                __syncwarp();
             }
-        }
-        TP_T(t1);
-        TP_ADD(0, t0, t1);
-        // ===== B. done when no chain is left in the CTA ===============================================================
-        if (__syncthreads_or(m >= 0) == 0) break;
-
-        // ===== C. positions -> shared memory (three bf16 parts), then the six tensor-core passes =======================
-#pragma unroll
-        for (int kc = 0; kc < (D + 7) / 8; ++kc) {
-            uint32_t w1[4], w2[4], w3[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j0 = kc * 8 + 2 * e;
-                const float x0 = (j0 < D) ? d[j0 < D ? j0 : 0] : 0.f;
-                const float x1 = (j0 + 1 < D) ? d[j0 + 1 < D ? j0 + 1 : 0] : 0.f;
-                split3(x0, x1, w1[e], w2[e], w3[e]);
+            store_slice(x, wide ? 7 : 6);
+            sh->red[slice][chain] = make_float2(hv, hk);
+            if (slice == 0 && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0 && (md == MODE_FIRST || md == MODE_MID)) {
+                // chain-0 trajectory capture (samplers.py:442-452): the point reached by this drift is row l+1
+                double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;
+                const int row = (md == MODE_FIRST) ? 1 : l + 1;
+                phi[2 * row] = (double)(x[0] + mu_s[0]); phi[2 * row + 1] = (double)(x[1] + mu_s[1]);
             }
-            const int off = (kc * TC_M + tid) * 16;
-            *reinterpret_cast<uint4*>(Ap + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-            *reinterpret_cast<uint4*>(Ap + TC_APART + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-            *reinterpret_cast<uint4*>(Ap + 2 * TC_APART + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+            TP_T(t2);
+            TP_ADD(1, t1, t2);
         }
-        TP_T(t2);
-        TP_ADD(1, t1, t2);
-        asm volatile("fence.proxy.async.shared::cta;");         // generic-proxy writes -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
+        TP_T(t3);
+
+        // ===== P2. per-chain bookkeeping by the slice-0 thread ==========================================================
+        if (slice == 0) {
+            int cmd = 0;
+            if (fetch && have_grad) {                      // the momentum requested in the previous pass has been drawn
+                Knew = 0.5f * sh->gK[chain]; L = sh->gL[chain]; lnu = sh->glnu[chain];
+                if (init) K0 = 0.5f * sh->gK0[chain];
+                n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
+                l = 0;
+                fetch = false;
+                if (a.phi_q && a.chain_id0 + m == 0 && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;   // samplers.py:444
+            }
+            if (have_grad && m >= 0 && sh->mode[chain] != MODE_IDLE) {
+                const int md = sh->mode[chain];
+                float sv = 0.f, sk = 0.f;
+#pragma unroll
+                for (int s2 = 0; s2 < TC_SPL; ++s2) { const float2 r = sh->red[s2][chain]; sv += r.x; sk += r.y; }
+                const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
+                const double V = 0.5 * (double)sv + vconst;                     // V(q) = 0.5 d.P d + const (utils.py:213-218)
+                if (md == MODE_FIRST) {
+                    if (init) {                                                 // samplers.py:416-420
+                        const double E0 = V + (double)K0;
+                        a.E_chain[(size_t)m * Lc] = E0;
+                        a.dE_chain[(size_t)m * Lc] = 0.0;
+                        E_prev = E0;
+                        init = false;
+                    }
+                    E_init = V + (double)Knew;                                  // samplers.py:434-438
+                    if (it >= a.warm_up_num) {
+                        const long idx = (it - a.warm_up_num) / a.thin_rate;
+                        a.E_chain[(size_t)m * Lc + idx] = E_init;
+                        a.dE_chain[(size_t)m * Lc + idx] = E_init - E_prev;
+                    }
+                    l = 1;
+                    sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
+                } else if (md == MODE_LAST) {
+                    // Metropolis accept (samplers.py:455-472)
+                    const double E_final = V + 0.5 * (double)sk;
+                    const double dE = E_final - E_init;
+                    E_prev = E_init;                                            // samplers.py:460
+                    const bool accepted = (dE < 0) || ((double)lnu < -dE);      // samplers.py:462
+                    const bool keep = it >= a.warm_up_num;
+                    if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
+                    else cmd |= CMD_RESTORE;
+                    if (keep) cmd |= CMD_STORE_OUT;
+                    sh->cm[chain] = (int)m;
+                    sh->cidx[chain] = keep ? (int)((it - a.warm_up_num) / a.thin_rate) : 0;
+                    if (tr) a.decision_chain[it - 1] = accepted ? 1 : 0;
+                    if (it >= a.iter_end) {                                     // chain finished (state_q holds its position)
+                        a.state_eprev[m] = E_prev;
+                        want = true;
+                    } else {
+                        it += 1;
+                        cmd |= CMD_REFRESH;
+                        sh->cit[chain] = it;
+                        fetch = true;
+                    }
+                    // the next gradient of a continuing chain is the first point of its new trajectory (position and
+                    // momentum are in place after P3, before the pass is issued)
+                    sh->mode[chain] = want ? MODE_IDLE : MODE_FIRST;
+                } else {
+                    l += 1;
+                    sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
+                }
+            }
+            if (want) {
+                // NOTE: a finished chain's STORE/RESTORE command is applied first (P3), the new chain is loaded in the
+                // next pass -- `want` stays set until then.
+                if (cmd == 0) {
+                    want = false;
+                    const unsigned int nxt = atomicAdd(queue, 1u);
+                    if (nxt < (unsigned int)a.Nchain) {
+                        m = (long)nxt;
+                        it = a.iter_begin + 1;
+                        init = (a.iter_begin == 0);
+                        if (!init) E_prev = a.state_eprev[m];
+                        if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
+                        cmd = CMD_NEW | CMD_REFRESH | (init ? CMD_INIT0 : 0);
+                        sh->cm[chain] = (int)m;
+                        sh->cit[chain] = it;
+                        fetch = true;
+                        sh->mode[chain] = MODE_FIRST;
+                    } else {
+                        m = -1;
+                        cmd = CMD_PARK;
+                        sh->mode[chain] = MODE_IDLE;
+                    }
+                }
+            }
+            sh->cmd[chain] = cmd;
+        }
+        __syncthreads();
+        TP_T(t4);
+        TP_ADD(2, t3, t4);
+
+        // ===== P3. apply the commands: sample store / restore / new chain (all four slice threads of a chain) =============
+        {
+            const int cmd = sh->cmd[chain];
+            if (cmd & (CMD_STORE_Q0 | CMD_STORE_OUT | CMD_RESTORE | CMD_NEW | CMD_PARK)) {
+                const long mc = sh->cm[chain];
+                const int nch4 = wide ? 7 : 6;
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.f;
+                if (cmd & CMD_PARK) {
+                    store_slice(x, nch4);
+#pragma unroll
+                    for (int j = 0; j < 28; ++j) p[j] = 0.f;
+                } else if (cmd & CMD_NEW) {
+                    const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + (size_t)mc * D + j0;
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) {
+                        if (c < nch4) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+                            if (a.iter_begin == 0) {
+                                *reinterpret_cast<float4*>(q0g + (size_t)mc * D + j0 + 4 * c) = v;
+                                *reinterpret_cast<float4*>(q_chain + (size_t)mc * Lc * D + j0 + 4 * c) = v;     // samplers.py:413
+                            }
+                            x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
+                            x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
+                        }
+                    }
+                    store_slice(x, nch4);
+                } else {
+                    float* dst = q_chain + ((size_t)mc * Lc + sh->cidx[chain]) * D + j0;
+                    float* q0 = q0g + (size_t)mc * D + j0;
+                    if (cmd & CMD_RESTORE) {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            if (c < nch4) {
+                                const float4 v = *reinterpret_cast<const float4*>(q0 + 4 * c);
+                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
+                                x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
+                                x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
+                            }
+                        }
+                        store_slice(x, nch4);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            if (c < nch4) {
+                                const float4 dd = Df[(j0 / 4 + c) * TC_M + chain];
+                                const float4 v = make_float4(dd.x + mu_s[j0 + 4 * c], dd.y + mu_s[j0 + 4 * c + 1],
+                                                             dd.z + mu_s[j0 + 4 * c + 2], dd.w + mu_s[j0 + 4 * c + 3]);
+                                *reinterpret_cast<float4*>(q0 + 4 * c) = v;
+                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- momentum refresh (samplers.py:431, 441, 461): the flagged chains of a 32-chain group are drawn by the four
+        //      warps of the group in turn, TC_SLOTS rows per round, then taken by the slice threads ------------------------
+        {
+            unsigned pending = __ballot_sync(HMC_FULL_MASK, (sh->cmd[chain] & CMD_REFRESH) != 0);
+            while (__syncthreads_or(pending != 0u)) {
+                unsigned todo = pending;
+                int k = 0;
+                unsigned taken = 0;
+                while (todo && k < TC_SLOTS) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if ((k & 3) == slice) {                       // this warp draws the k-th flagged chain of its group
+                        const int cs = grp * 32 + src;
+                        const long m_s = sh->cm[cs];
+                        const int it_s = sh->cit[cs];
+                        const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
+                        float* st = stage_all + (grp * TC_SLOTS + k) * 128;
+                        float ks, ln; int Lx;
+                        if (sh->cmd[cs] & CMD_INIT0) {            // samplers.py:415: chain-start momentum, K only
+                            tc_gen(ga, m_s, gid, 0, lane, st, &ks, &Lx, &ln);
+                            if (lane == 0) sh->gK0[cs] = ks;
+                            __syncwarp();
+                        }
+                        tc_gen(ga, m_s, gid, it_s, lane, st, &ks, &Lx, &ln);
+                        if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
+                    }
+                    taken |= 1u << src;
+                    ++k;
+                }
+                __syncthreads();
+                if (taken & (1u << lane)) {                       // my chain's row is staged: take my slice
+                    const int kk = __popc(taken & ((1u << lane) - 1u));
+                    const float* st = stage_all + (grp * TC_SLOTS + kk) * 128 + j0;
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) {
+                        if (c < 6 || wide) {
+                            const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
+                            p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+                        }
+                    }
+                }
+                pending &= ~taken;
+                __syncthreads();
+            }
+        }
+        TP_T(t5);
+        TP_ADD(3, t4, t5);
+
+        // ===== P4. done?  otherwise issue the next gradient pass ==========================================================
+        const bool alive = (slice == 0) && (m >= 0 || want);
+        asm volatile("fence.proxy.async.shared::cta;");         // generic-proxy writes of the operand rows -> tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        if (__syncthreads_or(alive) == 0) break;
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t a0 = smem_u32(Ap), b0 = smem_u32(Bp);
@@ -300,117 +533,9 @@ __global__ void __launch_bounds__(TC_M, 1) hmc_random_tc_kernel(const hmc_random
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
         }
-        {
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile("{\n\t.reg .pred pw;\n\tmbarrier.try_wait.parity.shared::cta.b64 pw, [%1], %2;\n\tselp.u32 %0, 1, 0, pw;\n\t}"
-                             : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
-            }
-            phase ^= 1u;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        TP_T(t3);
-        TP_ADD(2, t2, t3);
-
-        // ===== D. thread-local leapfrog update (samplers.py:835-837) and energies ======================================
-        // point index l of the gradient just evaluated: 0 = first point (half kick, drift), L = last (half kick, no
-        // drift), otherwise interior (second half kick of step l + first half kick of step l+1, drift).
-        const bool running = m >= 0;
-        const bool first = running && l == 0, last = running && l == L;
-        const float kwt = running ? ((first || last) ? -0.5f : -1.0f) : 0.f;
-        const float dwt = (running && !last) ? 1.f : 0.f;
-        float hv = 0.f, hk = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < KP; c0 += 16) {
-            if (c0 < D) {
-                uint32_t v[16];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                             : "r"(tmem_row + (uint32_t)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;");
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int j = c0 + c;
-                    if (j < D) {
-                        const float gj = __uint_as_float(v[c]);
-                        const float dtj = udt ? dt0 : dt_s[j];
-                        hv = fmaf(d[j], gj, hv);
-                        const float pn = fmaf(gj, kwt * dtj, p[j]);
-                        hk = fmaf(pn, pn, hk);
-                        p[j] = pn;
-                        d[j] = fmaf(pn, dwt * dtj, d[j]);
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;");      // TMEM reads ordered before the next pass's MMA
-
-        TP_T(t4);
-        TP_ADD(3, t3, t4);
-        // ===== E. per-thread bookkeeping ================================================================================
-        if (running) {
-            const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
-            const double V = 0.5 * (double)hv + vconst;                     // V(q) = 0.5 d.P d + const (utils.py:213-218)
-            if (first) {
-                if (init) {                                                 // samplers.py:416-420
-                    const double E0 = V + (double)K0;
-                    a.E_chain[(size_t)m * Lc] = E0;
-                    a.dE_chain[(size_t)m * Lc] = 0.0;
-                    E_prev = E0;
-                    init = false;
-                }
-                E_init = V + (double)Knew;                                  // samplers.py:434-438
-                if (it >= a.warm_up_num) {
-                    const long idx = (it - a.warm_up_num) / a.thin_rate;
-                    a.E_chain[(size_t)m * Lc + idx] = E_init;
-                    a.dE_chain[(size_t)m * Lc + idx] = E_init - E_prev;
-                }
-                l = 1;
-                if (tr) { double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2; phi[2] = (double)(d[0] + mu_s[0]); phi[3] = (double)(d[1] + mu_s[1]); }
-            } else if (last) {
-                // Metropolis accept (samplers.py:455-472)
-                const double E_final = V + 0.5 * (double)hk;
-                const double dE = E_final - E_init;
-                E_prev = E_init;                                            // samplers.py:460
-                const bool accepted = (dE < 0) || ((double)lnu < -dE);      // samplers.py:462
-                const bool keep = it >= a.warm_up_num;
-                const long idx = keep ? (it - a.warm_up_num) / a.thin_rate : 0;
-                float* dst = q_chain + ((size_t)m * Lc + idx) * D;
-                float* q0 = q0g + (size_t)m * D;
-                if (accepted) {
-                    if (keep) n_acc_post++; else n_acc_warm++;
-#pragma unroll
-                    for (int j4 = 0; j4 < D / 4; ++j4) {
-                        const float4 v = make_float4(d[4 * j4] + mu_s[4 * j4], d[4 * j4 + 1] + mu_s[4 * j4 + 1],
-                                                     d[4 * j4 + 2] + mu_s[4 * j4 + 2], d[4 * j4 + 3] + mu_s[4 * j4 + 3]);
-                        *reinterpret_cast<float4*>(q0 + 4 * j4) = v;
-                        if (keep) *reinterpret_cast<float4*>(dst + 4 * j4) = v;
-                    }
-                } else {
-#pragma unroll
-                    for (int j4 = 0; j4 < D / 4; ++j4) {
-                        const float4 v = *reinterpret_cast<const float4*>(q0 + 4 * j4);
-                        if (keep) *reinterpret_cast<float4*>(dst + 4 * j4) = v;
-                        d[4 * j4] = v.x - mu_s[4 * j4]; d[4 * j4 + 1] = v.y - mu_s[4 * j4 + 1];
-                        d[4 * j4 + 2] = v.z - mu_s[4 * j4 + 2]; d[4 * j4 + 3] = v.w - mu_s[4 * j4 + 3];
-                    }
-                }
-                if (tr) a.decision_chain[it - 1] = accepted ? 1 : 0;
-                if (it >= a.iter_end) {                                     // chain finished (state_q holds its position)
-                    a.state_eprev[m] = E_prev;
-                    want = true;
-                } else {
-                    it += 1;
-                    refresh = true;
-                }
-            } else {
-                l += 1;
-                if (tr) { double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2; phi[2 * l] = (double)(d[0] + mu_s[0]); phi[2 * l + 1] = (double)(d[1] + mu_s[1]); }
-            }
-        }
-        TP_T(t5);
-        TP_ADD(4, t4, t5);
+        have_grad = true;
+        TP_T(t6);
+        TP_ADD(4, t5, t6);
 #ifdef HMC_PROFILE_PHASES
         tph[5] += 1;
 #endif
@@ -442,6 +567,11 @@ extern "C" int hmc_debug_tc_cycles(unsigned long long* out8, int reset) {
 }
 #endif
 
+static size_t tc_smem_bytes() {
+    return 3 * (size_t)TC_APART + 3 * (size_t)TC_BPART + (size_t)TC_DCH * TC_M * 16 + sizeof(float) * (2 * TC_KP + 4 * TC_SLOTS * 128) +
+           sizeof(TcShared) + 64;
+}
+
 bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
     if (a.target.Mit || a.target.Pt || a.target.Lct) { *why = "identity momentum metric only"; return false; }
@@ -452,16 +582,16 @@ bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
 }
 
 int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
-    const size_t smem = 3 * (size_t)TC_APART + 3 * (size_t)TC_BPART + sizeof(float) * (2 * TC_KP + 4 * 128) + 64;
+    const size_t smem = tc_smem_bytes();
     HMC_CUDA_CHECK(cudaFuncSetAttribute(hmc_random_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     HMC_CUDA_CHECK(cudaGetDevice(&dev));
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (a.Nchain + TC_M - 1) / TC_M;
-    if (grid > sms) grid = sms;                 // persistent: one CTA per SM, threads pull chains from the queue
+    if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
     unsigned int* queue = (unsigned int*)a.state_g;
     HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
-    hmc_random_tc_kernel<<<grid, TC_M, smem, stream>>>(a, queue);
+    hmc_random_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(a, queue);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }
