@@ -52,5 +52,5 @@ e1.record(); torch.cuda.synchronize()
 out = (C.c_ulonglong * 8)()
 lib.hmc_debug_tc_cycles(out, 0)
 v = np.array(list(out), dtype=float); steps = v[5]
-print("tensor-core kernel (128 chains/CTA, 4 threads per chain): %.2f ms; warp-passes %d; cycles per pass: wait for MMA %.0f, TMEM read + leapfrog update + re-split %.0f, bookkeeping %.0f, apply commands + momentum refresh %.0f, fence + sync + MMA issue %.0f"
-      % (e0.elapsed_time(e1), steps, v[0] / steps, v[1] / steps, v[2] / steps, v[3] / steps, v[4] / steps))
+print("tensor-core kernel (128 chains/CTA, 4 threads per chain): %.2f ms; warp-passes %d; cycles per pass: wait for MMA %.0f, TMEM read + leapfrog update + re-split %.0f, sync + bookkeeping + sync %.0f, MMA issue (issuing warp only) %.0f, apply commands (stores / restores / new chains, take) %.0f, late momentum draws %.0f, draw-ahead (incl. group barrier) %.0f"
+      % (e0.elapsed_time(e1), steps, v[0] / steps, v[1] / steps, v[2] / steps, v[4] / (steps / 16), v[6] / steps, (v[3] - v[6]) / steps, v[7] / steps))

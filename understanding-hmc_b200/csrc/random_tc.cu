@@ -2,27 +2,42 @@
 //
 // Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839).
 //
-// One CTA = 128 chains, 512 threads.  The gradient of all 128 chains,
+// One CTA = 128 chains: 512 worker threads + one warp that only issues MMAs.  The gradient of all 128 chains,
 //       G[128 x N] = Dm[128 x K] * F[N x K]^T          (K = N = 112: D = 100 zero-padded to a multiple of 16)
-// runs on the 5th-generation tensor cores: the shifted positions d = q - mu are kept in shared memory as three bf16
-// parts (d = d1 + d2 + d3 exactly), the force matrix is split once the same way, and six tcgen05.mma passes
-// (1,3) (3,1) (2,2) (1,2) (2,1) (1,1) accumulate in fp32 in tensor memory -- the dropped terms are O(2^-24).
-// Shared-memory operands use the canonical no-swizzle K-major layout: 16-byte chunk (kc, row) at (kc*rows + row)*16
-// (LBO = rows*16 between K chunks, SBO = 128 between 8-row groups), so per-thread row writes are conflict-free
-// 128-bit stores.
+// runs on the 5th-generation tensor cores.  The shifted positions d = q - mu are split into three bf16 parts
+// (d = d1 + d2 + d3 exactly) that live in TENSOR MEMORY (A operand from TMEM, written with tcgen05.st: row = TMEM lane
+// = chain, two bf16 per 32-bit column); the force matrix is split once the same way into shared memory (canonical
+// no-swizzle K-major layout: 16-byte chunk (kc, row) at (kc*rows + row)*16, LBO = rows*16, SBO = 128).  Six
+// tcgen05.mma passes (1,3) (3,1) (2,2) (1,2) (2,1) (1,1) accumulate in fp32 in tensor memory -- the dropped terms
+// are O(2^-24).  Keeping A out of shared memory halves the tensor pipe's shared-memory traffic (an SS-mode pass reads
+// 7.5 KB per MMA = the whole shared-memory bandwidth, which starves everything that runs beside it).
 //
-// The accumulator row of chain c is TMEM lane c.  FOUR threads share a chain: thread (warp w, lane) works on chain
-// 32*(w%4) + lane (the TMEM lanes a warp may read) and on the dimension slice w/4 (24, 24, 24, 28 dims): it reads
-// its slice of the gradient with tcgen05.ld, keeps the momentum slice in registers, updates the position slice
-// (fp32 copy in shared memory) and re-splits it.  Per-chain sums (d.g, p.p) are combined through shared memory by
-// the slice-0 thread, which does the chain's bookkeeping (energies, Metropolis accept on a Philox uniform, new
-// trajectory length) and posts a command that all four slice threads apply (sample store, restore, momentum
-// refresh).  Every chain advances one gradient evaluation per pass; iteration boundaries are per-chain events
-// (SURVEY H3); the first point of each trajectory is a gradient-only pass, so an iteration costs L + 1
-// evaluations.  Momentum refresh is warp-cooperative (one Philox call per lane, same draws as every other kernel);
-// finished chains pull the next chain from a global queue.
+// FOUR threads share a chain: thread (warp w, lane) works on chain 32*(w%4) + lane (the TMEM lanes a warp may
+// access) and on the dimension slice w/4 (24, 24, 24, 28 dims).  Position and momentum slices stay in registers; a
+// pass is: read the slice of the gradient (tcgen05.ld), leapfrog update, re-split, tcgen05.st.  Per-chain sums
+// (d.g, p.p) are combined through shared memory by the slice-0 thread, which does the chain's bookkeeping
+// (energies, Metropolis accept on a Philox uniform, new trajectory length) and posts a command that all four slice
+// threads apply (sample store, restore, momentum take).  Every chain advances one gradient evaluation per pass;
+// iteration boundaries are per-chain events; the first point of each trajectory is a gradient-only pass,
+// so an iteration costs L + 1 evaluations.
+//
+// Schedule of a pass (n):   P1 consume G(n-1) | S1 | issuing warp: MMA(n)  ||  workers: P2 bookkeeping, group barrier,
+// P3 commands, D momentum draws | P1 ...   The MMA is issued from the rows as they stand after P1, so everything else
+// runs under it.  A rejected chain's row is rewritten under the running pass: its first gradient is taken one pass
+// later.  The next momentum of a chain is drawn while its LAST gradient is in flight (the draw does not depend on the
+// accept decision: samplers.py:431, 441 draw p, L, u at the top of every iteration), warp-cooperatively (one Philox
+// call per lane, same draws as every other kernel) into the chain's staging row.  Finished chains pull the next
+// chain from a global queue.
 #include "hmc_common.cuh"
 #include <cuda_bf16.h>
+
+#ifdef HMC_TC_DEBUG
+// progress markers in mapped host memory (readable while a kernel hangs): g_tc_dbg[warp] = pass * 100 + stage, block 0 only
+__device__ volatile int* g_tc_dbg = nullptr;
+#define TC_MARK(stage) do { if (g_tc_dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) { g_tc_dbg[threadIdx.x >> 5] = dbg_pass * 100 + (stage); __threadfence_system(); } } while (0)
+#else
+#define TC_MARK(stage)
+#endif
 
 #ifdef HMC_PROFILE_PHASES
 __device__ unsigned long long g_tc_cycles[8];
@@ -40,16 +55,24 @@ constexpr int TC_KP = 112;          // padded K = N (multiple of 16)
 constexpr int TC_KC = TC_KP / 8;    // 16-byte chunks (8 bf16) per operand row
 constexpr int TC_M = 128;           // chains per CTA
 constexpr int TC_SPL = 4;           // threads (dimension slices) per chain
-constexpr int TC_THREADS = TC_M * TC_SPL;
-constexpr int TC_APART = TC_KC * TC_M * 16;     // bytes of one A part
+constexpr int TC_THREADS = TC_M * TC_SPL;       // worker threads
+constexpr int TC_NT = TC_THREADS + 128;         // + one warpgroup whose first warp only issues the MMAs (the issuing thread
+                                                // is held while the tensor pipe drains; a worker in that role stalls the
+                                                // whole CTA).  A whole warpgroup, so that it can hand its registers to the
+                                                // workers (setmaxnreg): 4 x 112 + 24 registers x 32 lanes per scheduler (of the 5 x 96 x 32 allocated at launch).
 constexpr int TC_BPART = TC_KC * TC_KP * 16;    // bytes of one B part
-constexpr int TC_DCH = TC_ND / 4;               // fp32 position chunks (4 dims) per chain
-constexpr int TC_SLOTS = 5;                     // momentum staging slots per 32-chain group and round
+constexpr uint32_t TC_ACOL = 128;               // first TMEM column of the A parts (accumulator: columns 0..111)
+constexpr uint32_t TC_APITCH = 64;              // TMEM columns per A part (56 used: K/2)
+constexpr int TC_SROW = TC_ND;                  // floats per momentum staging row (one row per chain)
 
-enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_REFRESH = 32, CMD_INIT0 = 64 };
+enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_REFRESH = 32, CMD_INIT0 = 64, CMD_TAKE = 128 };
 enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// named barriers: 1..4 = the four warps of a 32-chain group, 5 = workers + issuing warp
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, %0;" ::"n"(TC_THREADS + 32) : "memory"); }
+__device__ __forceinline__ void bar_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -70,6 +93,62 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& h1, uint32_
     r0 -= __uint_as_float(h2 << 16); r1 -= __uint_as_float(h2 & 0xffff0000u);
     __nv_bfloat162 c = __floats2bfloat162_rn(r0, r1);
     h3 = *reinterpret_cast<uint32_t*>(&c);
+}
+
+// tensor-memory stores of one warp: lane i writes TMEM lane (32 * (warp % 4) + i), consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t addr, const uint32_t* w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w[0]), "r"(w[1]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// positions x[0..16) of a slice -> the three bf16 parts, TMEM columns acol .. acol+7 of each part
+__device__ __forceinline__ void put_half0(uint32_t acol, const float* x) {
+    uint32_t w1[8], w2[8], w3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split3(x[2 * e], x[2 * e + 1], w1[e], w2[e], w3[e]);
+    tmem_st8(acol, w1); tmem_st8(acol + TC_APITCH, w2); tmem_st8(acol + 2 * TC_APITCH, w3);
+}
+// positions x[16..24) (x[16..28) for the wide slice) -> columns acol+8 .. acol+11 (.. acol+13)
+__device__ __forceinline__ void put_half1(uint32_t acol, const float* x, bool wide) {
+    uint32_t w1[6], w2[6], w3[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) split3(x[16 + 2 * e], x[17 + 2 * e], w1[e], w2[e], w3[e]);
+    tmem_st4(acol + 8, w1); tmem_st4(acol + 8 + TC_APITCH, w2); tmem_st4(acol + 8 + 2 * TC_APITCH, w3);
+    if (wide) { tmem_st2(acol + 12, w1 + 4); tmem_st2(acol + 12 + TC_APITCH, w2 + 4); tmem_st2(acol + 12 + 2 * TC_APITCH, w3 + 4); }
+}
+
+// The 42 MMAs of a gradient pass: six part products, small terms first: (1,3) (3,1) (2,2) (1,2) (2,1) (1,1), seven
+// K steps each.  A from tensor memory (part pa, 8 columns per K step), B descriptor = constant high word + start address
+// (>> 4) in the low word; the per-MMA offsets are immediates inside the asm so that nothing is hoisted into registers.
+template <int I>
+__device__ __forceinline__ void tc_mma_all(uint32_t tmem, uint32_t dlo, uint32_t dhi, uint32_t idesc) {
+    if constexpr (I < 6 * (TC_KP / 16)) {
+        constexpr int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {2, 0, 1, 1, 0, 0};
+        constexpr int t = I / (TC_KP / 16), ks = I % (TC_KP / 16);
+        asm volatile(
+            "{\n\t.reg .pred pacc;\n\t.reg .b32 ta, bl;\n\t.reg .b64 db;\n\t"
+            "setp.ne.b32 pacc, %4, 0;\n\t"
+            "add.u32 ta, %0, %5;\n\t"
+            "add.u32 bl, %1, %6;\n\t"
+            "mov.b64 db, {bl, %2};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, {%7, %7, %7, %7}, pacc;\n\t}"
+            ::"r"(tmem), "r"(dlo), "r"(dhi), "r"(idesc), "r"(I ? 1u : 0u),
+              "n"((int)(TC_ACOL + pa[t] * TC_APITCH + 8 * ks)), "n"((pb[t] * TC_BPART + ks * 2 * TC_KP * 16) >> 4), "r"(0u));
+        tc_mma_all<I + 1>(tmem, dlo, dhi, idesc);
+    }
 }
 
 struct TcGen {
@@ -124,39 +203,42 @@ struct TcShared {                       // small per-chain arrays in shared memo
     float2 red[TC_SPL][TC_M];           // partial (d.g, p.p) per slice
     int mode[TC_M];                     // MODE_* of the gradient being evaluated
     int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread
-    int cm[TC_M];                       // local chain index the command refers to (row addressing)
+    int cm[TC_M];                       // local chain index of the chain in this slot
     int cidx[TC_M];                     // stored-sample index of the command
-    int cit[TC_M];                      // iteration whose momentum is to be drawn
+    int cit[TC_M];                      // iteration whose momentum is to be drawn: set with MODE_LAST for the draw ahead
+                                        // (0 = the chain ends with this trajectory), and by the late path (new chains)
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
     int gL[TC_M];
+    int galive[2][4];                   // per pass parity and group: some slot still has (or wants) a chain
+    int nleft[4];                       // per group: late momentum draws requested in this pass
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
+__global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* Ap = smem;                                   // 3 parts [KC][128] 16-byte chunks
-    unsigned char* Bp = Ap + 3 * TC_APART;                      // 3 parts [KC][112]
-    float4* Df = reinterpret_cast<float4*>(Bp + 3 * TC_BPART);  // fp32 positions [TC_DCH][128] 16-byte chunks
-    float* mu_s = reinterpret_cast<float*>(Df + TC_DCH * TC_M); // [KP]
+    unsigned char* Bp = smem;                                   // 3 parts [KC][112] 16-byte chunks
+    float* mu_s = reinterpret_cast<float*>(Bp + 3 * TC_BPART);  // [KP]
     float* dt_s = mu_s + KP;                                    // [KP]
-    float* stage_all = dt_s + KP;                               // [4 groups][TC_SLOTS][128] momentum staging
-    TcShared* sh = reinterpret_cast<TcShared*>(stage_all + 4 * TC_SLOTS * 128);
+    float* stage_all = dt_s + KP;                               // [128][TC_SROW] momentum staging, one row per chain
+    TcShared* sh = reinterpret_cast<TcShared*>(stage_all + TC_M * TC_SROW);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sh + 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef HMC_TC_DEBUG
+    int dbg_pass = 0;
+#endif
+    TC_MARK(1);
     const int grp = warp & 3;                    // 32-chain group == TMEM lane quarter this warp may access
-    const int slice = warp >> 2;                 // dimension slice
+    const int slice = warp >> 2;                 // dimension slice (4 = the issuing warpgroup)
     const int chain = grp * 32 + lane;           // chain slot of this thread
-    const int j0 = 24 * slice;                   // first dimension of the slice
+    const int j0 = 24 * (slice & 3);             // first dimension of the slice
     const bool wide = slice == TC_SPL - 1;       // the last slice has 28 dims, the others 24
 
     // ---- one-time set-up ---------------------------------------------------------------------------------------------
-    for (int t = tid; t < 3 * TC_APART / 16; t += TC_THREADS) reinterpret_cast<uint4*>(Ap)[t] = make_uint4(0u, 0u, 0u, 0u);
-    for (int t = tid; t < TC_DCH * TC_M; t += TC_THREADS) Df[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         const float* Ft = (const float*)a.target.Ft;            // Ft[k][n] = F[n][k]; B row n holds F[n][.] (K-major)
         const int Dpad = a.target.D_pad;
-        for (int t = tid; t < KC * KP; t += TC_THREADS) {       // one 16-byte chunk (8 k values) of row n per item
+        for (int t = tid; t < KC * KP; t += TC_NT) {            // one 16-byte chunk (8 k values) of row n per item
             const int kc = t / KP, n = t % KP;
             uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
@@ -170,25 +252,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
             reinterpret_cast<uint4*>(Bp + TC_BPART)[t] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
             reinterpret_cast<uint4*>(Bp + 2 * TC_BPART)[t] = make_uint4(w3[0], w3[1], w3[2], w3[3]);
         }
-        for (int t = tid; t < KP; t += TC_THREADS) {
+        for (int t = tid; t < KP; t += TC_NT) {
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = tid; t < TC_M; t += TC_THREADS) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; }
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->cit[t] = 0; sh->cm[t] = 0; }
+        if (tid < 8) sh->galive[tid >> 2][tid & 3] = 1;
+        if (tid < 4) sh->nleft[tid] = 0;
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    TC_MARK(2);
+    asm volatile("fence.proxy.async.shared::cta;");             // B parts (generic-proxy writes) -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_row = tmem + ((uint32_t)(grp * 32) << 16) + (uint32_t)j0;
+    TC_MARK(3);
+    const uint32_t tmem_row = tmem + ((uint32_t)(grp * 32) << 16) + (uint32_t)j0;                   // my accumulator slice
+    const uint32_t acol = tmem + ((uint32_t)(grp * 32) << 16) + TC_ACOL + 12u * (uint32_t)(slice & 3);  // my A-part columns
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
@@ -199,16 +287,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
     ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
 
+    if (slice >= TC_SPL) {
+        // ===== the issuing warpgroup: hands its registers to the workers (per scheduler: 4 x 112 + 24 registers x 32 lanes
+        //       = 16 K).  Its first warp launches, after every S1 barrier, the gradient pass of the operand rows as they
+        //       stand; the workers' bookkeeping, commands and momentum draws run under it. =====================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        TC_MARK(4);
+        if (warp == TC_THREADS / 32) {                        // the other three warps of the group only gave their registers
+            int par = 0;
+#ifdef HMC_PROFILE_PHASES
+            long long tph4 = 0;
+#endif
+            while (true) {
+                TC_MARK(10);
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                bar_all();
+                TC_MARK(11);
+                const volatile int* ga_ = sh->galive[par ^ 1];
+                if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
+                par ^= 1;
+                if (lane == 0) {
+    #ifdef HMC_PROFILE_PHASES
+                    const long long ti0 = clock64();
+    #endif
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint64_t dsc = make_desc(smem_u32(Bp), KP * 16, 128);
+                    const uint32_t dlo = (uint32_t)dsc, dhi = (uint32_t)(dsc >> 32);
+                    tc_mma_all<0>(tmem, dlo, dhi, idesc);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+    #ifdef HMC_PROFILE_PHASES
+                    tph4 += clock64() - ti0;
+    #endif
+                }
+                TC_MARK(12);
+#ifdef HMC_TC_DEBUG
+                ++dbg_pass;
+#endif
+                __syncwarp();
+            }
+#ifdef HMC_PROFILE_PHASES
+            if (lane == 0) atomicAdd(&g_tc_cycles[4], (unsigned long long)tph4);
+#endif
+        }
+        __syncthreads();
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    TC_MARK(5);
+
     // ---- per-thread state -----------------------------------------------------------------------------------------------
-    float p[28];                     // momentum slice (registers)
+    float p[28], x[28];              // momentum and shifted-position (q - mu) slices, registers
 #pragma unroll
-    for (int j = 0; j < 28; ++j) p[j] = 0.f;
+    for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
     // bookkeeping state of chain `chain`, used by the slice-0 thread only
     long m = -1;                     // local chain index, -1 = no chain
     int it = 0, l = 0, L = 1;        // iteration, point index of the next gradient, trajectory length
     bool init = false;               // chain start: E_chain[.,0] still to be recorded
     bool want = (slice == 0);        // needs a (new) chain
-    bool fetch = false;              // momentum of iteration `it` was requested, results are in sh->g*
+    bool fetch = false;              // momentum of iteration `it` was requested on the late path, results are in sh->g*
+    bool delayed = false;            // operand row rewritten under the running pass: first gradient one pass later
+    int par = 0;                     // pass parity
     double E_init = 0.0, E_prev = 0.0;
     float K0 = 0.f, Knew = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
@@ -218,28 +356,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
-    // position slice helpers -------------------------------------------------------------------------------------------------
-    // write the slice [j0, j0+nj) of the fp32 row and re-split it into the three bf16 parts (8-dim operand chunks)
-    auto store_slice = [&](const float (&x)[32], int nch4) {
+    if (slice < TC_SPL) {            // defined operand rows before the first pass: all parts zero (K padding included)
+        put_half0(acol, x);
+        put_half1(acol, x, true);    // the wide form also clears columns 12, 13 of the slice; harmless for the others
+        if (wide) {                  // K padding: dims 100..111 = columns 50..55 of each part
+            const uint32_t z[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int c = 0; c < 7; ++c)
-            if (c < nch4) Df[(j0 / 4 + c) * TC_M + chain] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-#pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-            if (kc < 3 || wide) {
-                uint32_t w1[4], w2[4], w3[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split3(x[8 * kc + 2 * e], x[8 * kc + 2 * e + 1], w1[e], w2[e], w3[e]);
-                const int off = ((j0 / 8 + kc) * TC_M + chain) * 16;
-                *reinterpret_cast<uint4*>(Ap + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-                *reinterpret_cast<uint4*>(Ap + TC_APART + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-                *reinterpret_cast<uint4*>(Ap + 2 * TC_APART + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+            for (int pt = 0; pt < 3; ++pt) {
+                tmem_st4(acol + 14 + pt * TC_APITCH, z);
+                tmem_st2(acol + 18 + pt * TC_APITCH, z);
             }
         }
-    };
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
 
+    TC_MARK(6);
     while (true) {
         TP_T(t0);
+        TC_MARK(20);
         // ===== P1. consume the gradient: thread-local leapfrog update of the slice (samplers.py:835-837) ==============
         if (have_grad) {
             {
@@ -251,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                 phase ^= 1u;
             }
             asm volatile("tcgen05.fence::after_thread_sync;");
+            TC_MARK(21);
             TP_T(t1);
             TP_ADD(0, t0, t1);
             const int md = sh->mode[chain];
@@ -258,34 +393,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
             // kick of step l + first half kick of step l+1, drift
             const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -1.0f : -0.5f);
             const float dwt = (md == MODE_FIRST || md == MODE_MID) ? 1.f : 0.f;
-            uint32_t gv[32];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7]),
-                           "=r"(gv[8]), "=r"(gv[9]), "=r"(gv[10]), "=r"(gv[11]), "=r"(gv[12]), "=r"(gv[13]), "=r"(gv[14]), "=r"(gv[15])
-                         : "r"(tmem_row));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(gv[16]), "=r"(gv[17]), "=r"(gv[18]), "=r"(gv[19]), "=r"(gv[20]), "=r"(gv[21]), "=r"(gv[22]), "=r"(gv[23]),
-                           "=r"(gv[24]), "=r"(gv[25]), "=r"(gv[26]), "=r"(gv[27]), "=r"(gv[28]), "=r"(gv[29]), "=r"(gv[30]), "=r"(gv[31])
-                         : "r"(tmem_row + 16u));
-            asm volatile("tcgen05.wait::ld.sync.aligned;");
-            asm volatile("tcgen05.fence::before_thread_sync;");      // TMEM reads ordered before the next MMA
-            float x[32];
-            float hv = 0.f, hk = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const bool on = c < 6 || (wide && c < 7);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (on) v = Df[(j0 / 4 + c) * TC_M + chain];
-                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-            }
-            if (slice == 0 && md == MODE_FIRST && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0) {
+            const bool tr = slice == 0 && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0;
+            if (tr && md == MODE_FIRST) {
                 double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;      // row 0: the start point (samplers.py:445)
                 phi[0] = (double)(x[0] + mu_s[0]); phi[1] = (double)(x[1] + mu_s[1]);
             }
+            float hv = 0.f, hk = 0.f;
+            uint32_t gv[16];
+            tmem_ld16(tmem_row, gv);
 #pragma unroll
-            for (int jj = 0; jj < 28; ++jj) {
+            for (int jj = 0; jj < 16; ++jj) {
+                const float gj = __uint_as_float(gv[jj]);
+                const float dtj = dt_s[j0 + jj];
+                hv = fmaf(x[jj], gj, hv);
+                const float pn = fmaf(gj, kwt * dtj, p[jj]);
+                hk = fmaf(pn, pn, hk);
+                p[jj] = pn;
+                x[jj] = fmaf(pn, dwt * dtj, x[jj]);
+            }
+            put_half0(acol, x);
+            tmem_ld16(tmem_row + 16u, gv);
+#pragma unroll
+            for (int jj = 16; jj < 28; ++jj) {
                 if (jj < 24 || wide) {
-                    const float gj = __uint_as_float(gv[jj]);
+                    const float gj = __uint_as_float(gv[jj - 16]);
                     const float dtj = dt_s[j0 + jj];
                     hv = fmaf(x[jj], gj, hv);
                     const float pn = fmaf(gj, kwt * dtj, p[jj]);
@@ -294,9 +425,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                     x[jj] = fmaf(pn, dwt * dtj, x[jj]);
                 }
             }
-            store_slice(x, wide ? 7 : 6);
+            put_half1(acol, x, wide);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             sh->red[slice][chain] = make_float2(hv, hk);
-            if (slice == 0 && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0 && (md == MODE_FIRST || md == MODE_MID)) {
+            if (tr && (md == MODE_FIRST || md == MODE_MID)) {
                 // chain-0 trajectory capture (samplers.py:442-452): the point reached by this drift is row l+1
                 double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;
                 const int row = (md == MODE_FIRST) ? 1 : l + 1;
@@ -305,13 +437,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
             TP_T(t2);
             TP_ADD(1, t1, t2);
         }
-        __syncthreads();
+        TC_MARK(22);
+        asm volatile("tcgen05.fence::before_thread_sync;");     // TMEM reads / writes ordered before the next MMA
+        bar_all();                                              // S1: releases the issuing warp
+        {
+            const volatile int* ga_ = sh->galive[par ^ 1];      // written in P2 of the previous pass
+            if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
+        }
+        have_grad = true;
+        TC_MARK(23);
         TP_T(t3);
 
         // ===== P2. per-chain bookkeeping by the slice-0 thread ==========================================================
         if (slice == 0) {
             int cmd = 0;
-            if (fetch && have_grad) {                      // the momentum requested in the previous pass has been drawn
+            if (fetch) {                                   // the momentum requested in the previous pass has been drawn
                 Knew = 0.5f * sh->gK[chain]; L = sh->gL[chain]; lnu = sh->glnu[chain];
                 if (init) K0 = 0.5f * sh->gK0[chain];
                 n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
@@ -319,12 +459,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                 fetch = false;
                 if (a.phi_q && a.chain_id0 + m == 0 && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;   // samplers.py:444
             }
-            if (have_grad && m >= 0 && sh->mode[chain] != MODE_IDLE) {
-                const int md = sh->mode[chain];
+            const int md = sh->mode[chain];
+            if (m >= 0 && md != MODE_IDLE) {
                 float sv = 0.f, sk = 0.f;
 #pragma unroll
                 for (int s2 = 0; s2 < TC_SPL; ++s2) { const float2 r = sh->red[s2][chain]; sv += r.x; sk += r.y; }
-                const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
+                const bool tr = a.phi_q && (a.chain_id0 + m) == 0;
                 const double V = 0.5 * (double)sv + vconst;                     // V(q) = 0.5 d.P d + const (utils.py:213-218)
                 if (md == MODE_FIRST) {
                     if (init) {                                                 // samplers.py:416-420
@@ -342,6 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                     }
                     l = 1;
                     sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
+                    if (l == L) sh->cit[chain] = (it < a.iter_end) ? it + 1 : 0;
                 } else if (md == MODE_LAST) {
                     // Metropolis accept (samplers.py:455-472)
                     const double E_final = V + 0.5 * (double)sk;
@@ -352,25 +493,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                     if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
                     if (keep) cmd |= CMD_STORE_OUT;
-                    sh->cm[chain] = (int)m;
                     sh->cidx[chain] = keep ? (int)((it - a.warm_up_num) / a.thin_rate) : 0;
-                    if (tr) a.decision_chain[it - 1] = accepted ? 1 : 0;
+                    if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
                     if (it >= a.iter_end) {                                     // chain finished (state_q holds its position)
                         a.state_eprev[m] = E_prev;
                         want = true;
-                    } else {
+                    } else {                                                    // momentum drawn ahead, under the last pass
                         it += 1;
-                        cmd |= CMD_REFRESH;
-                        sh->cit[chain] = it;
-                        fetch = true;
+                        Knew = 0.5f * sh->gK[chain]; L = sh->gL[chain]; lnu = sh->glnu[chain];
+                        n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
+                        l = 0;
+                        if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                 // samplers.py:444
+                        cmd |= CMD_TAKE;
                     }
-                    // the next gradient of a continuing chain is the first point of its new trajectory (position and
-                    // momentum are in place after P3, before the pass is issued)
-                    sh->mode[chain] = want ? MODE_IDLE : MODE_FIRST;
+                    // the next gradient of a continuing chain is the first point of its new trajectory.  This pass is
+                    // already running: an accepted chain's operand row is right, a rejected chain's row is rewritten
+                    // under the pass, so its first gradient is taken one pass later.
+                    if (want || !accepted) { sh->mode[chain] = MODE_IDLE; delayed = !want; }
+                    else sh->mode[chain] = MODE_FIRST;
                 } else {
                     l += 1;
                     sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
+                    if (l == L) sh->cit[chain] = (it < a.iter_end) ? it + 1 : 0;
                 }
+            } else if (delayed) {
+                delayed = false;
+                sh->mode[chain] = MODE_FIRST;
             }
             if (want) {
                 // NOTE: a finished chain's STORE/RESTORE command is applied first (P3), the new chain is loaded in the
@@ -388,7 +536,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                         sh->cm[chain] = (int)m;
                         sh->cit[chain] = it;
                         fetch = true;
-                        sh->mode[chain] = MODE_FIRST;
+                        sh->mode[chain] = MODE_IDLE;            // row loaded under the running pass
+                        delayed = true;
                     } else {
                         m = -1;
                         cmd = CMD_PARK;
@@ -397,24 +546,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                 }
             }
             sh->cmd[chain] = cmd;
+            const int alive = __any_sync(HMC_FULL_MASK, m >= 0 || want);
+            const int late = __any_sync(HMC_FULL_MASK, (cmd & CMD_REFRESH) != 0);
+            if (lane == 0) { sh->galive[par][grp] = alive; sh->nleft[grp] = late; }
         }
-        __syncthreads();
-        TP_T(t4);
-        TP_ADD(2, t3, t4);
+        TC_MARK(24);
+        bar_group(grp);
+        TC_MARK(25);
+        TP_T(t4a);
+        TP_ADD(2, t3, t4a);
 
-        // ===== P3. apply the commands: sample store / restore / new chain (all four slice threads of a chain) =============
+        // ===== P3. apply the commands: momentum take, sample store / restore / new chain (all four slice threads) ==========
         {
             const int cmd = sh->cmd[chain];
+            const int nch4 = wide ? 7 : 6;
+            if (cmd & CMD_TAKE) {                                   // momentum drawn ahead: take my slice of the chain's row
+                const float* st = stage_all + chain * TC_SROW + j0;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    if (c < nch4) {
+                        const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
+                        p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+                    }
+                }
+            }
             if (cmd & (CMD_STORE_Q0 | CMD_STORE_OUT | CMD_RESTORE | CMD_NEW | CMD_PARK)) {
                 const long mc = sh->cm[chain];
-                const int nch4 = wide ? 7 : 6;
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = 0.f;
                 if (cmd & CMD_PARK) {
-                    store_slice(x, nch4);
 #pragma unroll
-                    for (int j = 0; j < 28; ++j) p[j] = 0.f;
+                    for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
                 } else if (cmd & CMD_NEW) {
                     const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + (size_t)mc * D + j0;
 #pragma unroll
@@ -429,7 +589,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                             x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
                         }
                     }
-                    store_slice(x, nch4);
                 } else {
                     float* dst = q_chain + ((size_t)mc * Lc + sh->cidx[chain]) * D + j0;
                     float* q0 = q0g + (size_t)mc * D + j0;
@@ -443,14 +602,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                                 x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
                             }
                         }
-                        store_slice(x, nch4);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 7; ++c) {
                             if (c < nch4) {
-                                const float4 dd = Df[(j0 / 4 + c) * TC_M + chain];
-                                const float4 v = make_float4(dd.x + mu_s[j0 + 4 * c], dd.y + mu_s[j0 + 4 * c + 1],
-                                                             dd.z + mu_s[j0 + 4 * c + 2], dd.w + mu_s[j0 + 4 * c + 3]);
+                                const float4 v = make_float4(x[4 * c] + mu_s[j0 + 4 * c], x[4 * c + 1] + mu_s[j0 + 4 * c + 1],
+                                                             x[4 * c + 2] + mu_s[j0 + 4 * c + 2], x[4 * c + 3] + mu_s[j0 + 4 * c + 3]);
                                 *reinterpret_cast<float4*>(q0 + 4 * c) = v;
                                 if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
                             }
@@ -458,95 +615,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
                     }
                 }
             }
-        }
-        // ---- momentum refresh (samplers.py:431, 441, 461): the flagged chains of a 32-chain group are drawn by the four
-        //      warps of the group in turn, TC_SLOTS rows per round, then taken by the slice threads ------------------------
-        {
-            unsigned pending = __ballot_sync(HMC_FULL_MASK, (sh->cmd[chain] & CMD_REFRESH) != 0);
-            while (__syncthreads_or(pending != 0u)) {
-                unsigned todo = pending;
+            // rewritten rows -> tensor memory.  tcgen05.st is warp-wide: the other lanes rewrite their unchanged rows.
+            if (__any_sync(HMC_FULL_MASK, (cmd & (CMD_RESTORE | CMD_NEW | CMD_PARK)) != 0)) {
+                put_half0(acol, x);
+                put_half1(acol, x, wide);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            TC_MARK(26);
+            TP_T(t4b);
+            TP_ADD(6, t4a, t4b);
+
+            // ---- late momentum draws (new chains: samplers.py:415, 431): the flagged chains of the group are drawn by its
+            //      four warps in turn, then taken by the slice threads -------------------------------------------------------
+            if (sh->nleft[grp]) {
+                unsigned todo = __ballot_sync(HMC_FULL_MASK, (cmd & CMD_REFRESH) != 0);
                 int k = 0;
-                unsigned taken = 0;
-                while (todo && k < TC_SLOTS) {
+                while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
                     if ((k & 3) == slice) {                       // this warp draws the k-th flagged chain of its group
                         const int cs = grp * 32 + src;
                         const long m_s = sh->cm[cs];
-                        const int it_s = sh->cit[cs];
                         const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
-                        float* st = stage_all + (grp * TC_SLOTS + k) * 128;
+                        float* st = stage_all + cs * TC_SROW;
                         float ks, ln; int Lx;
                         if (sh->cmd[cs] & CMD_INIT0) {            // samplers.py:415: chain-start momentum, K only
                             tc_gen(ga, m_s, gid, 0, lane, st, &ks, &Lx, &ln);
                             if (lane == 0) sh->gK0[cs] = ks;
                             __syncwarp();
                         }
-                        tc_gen(ga, m_s, gid, it_s, lane, st, &ks, &Lx, &ln);
+                        tc_gen(ga, m_s, gid, sh->cit[cs], lane, st, &ks, &Lx, &ln);
                         if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
                     }
-                    taken |= 1u << src;
                     ++k;
                 }
-                __syncthreads();
-                if (taken & (1u << lane)) {                       // my chain's row is staged: take my slice
-                    const int kk = __popc(taken & ((1u << lane) - 1u));
-                    const float* st = stage_all + (grp * TC_SLOTS + kk) * 128 + j0;
+                bar_group(grp);
+                if (cmd & CMD_REFRESH) {
+                    const float* st = stage_all + chain * TC_SROW + j0;
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
-                        if (c < 6 || wide) {
+                        if (c < nch4) {
                             const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
                             p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
                         }
                     }
                 }
-                pending &= ~taken;
-                __syncthreads();
             }
         }
+        TC_MARK(27);
         TP_T(t5);
-        TP_ADD(3, t4, t5);
+        TP_ADD(3, t4a, t5);
 
-        // ===== P4. done?  otherwise issue the next gradient pass ==========================================================
-        const bool alive = (slice == 0) && (m >= 0 || want);
-        asm volatile("fence.proxy.async.shared::cta;");         // generic-proxy writes of the operand rows -> tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        if (__syncthreads_or(alive) == 0) break;
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t a0 = smem_u32(Ap), b0 = smem_u32(Bp);
-            // small terms first: (1,3) (3,1) (2,2) (1,2) (2,1) (1,1)
-            const int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {2, 0, 1, 1, 0, 0};
-            uint32_t acc = 0;
-#pragma unroll
-            for (int t = 0; t < 6; ++t) {
-#pragma unroll
-                for (int ks = 0; ks < KP / 16; ++ks) {
-                    const uint64_t da = make_desc(a0 + pa[t] * TC_APART + ks * 2 * TC_M * 16, TC_M * 16, 128);
-                    const uint64_t db = make_desc(b0 + pb[t] * TC_BPART + ks * 2 * KP * 16, KP * 16, 128);
-                    asm volatile(
-                        "{\n\t.reg .pred pacc;\n\tsetp.ne.b32 pacc, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, pacc;\n\t}"
-                        ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u));
-                    acc = 1;
+        // ===== D. draw ahead: the next momentum of every chain whose final gradient is in flight (samplers.py:431, 441),
+        //      into the chain's own staging row; the four warps of the group share the draws ===================================
+        {
+            unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->mode[chain] == MODE_LAST && sh->cit[chain] > 0);
+            int k = 0;
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                if ((k & 3) == slice) {
+                    const int cs = grp * 32 + src;
+                    const long m_s = sh->cm[cs];
+                    float ks, ln; int Lx;
+                    tc_gen(ga, m_s, (uint64_t)(a.chain_id0 + m_s), sh->cit[cs], lane, stage_all + cs * TC_SROW, &ks, &Lx, &ln);
+                    if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
                 }
+                ++k;
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
         }
-        have_grad = true;
+        par ^= 1;
+        TC_MARK(28);
+#ifdef HMC_TC_DEBUG
+        ++dbg_pass;
+#endif
         TP_T(t6);
-        TP_ADD(4, t5, t6);
+        TP_ADD(7, t5, t6);
 #ifdef HMC_PROFILE_PHASES
         tph[5] += 1;
 #endif
     }
 #ifdef HMC_PROFILE_PHASES
-    if (lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(&g_tc_cycles[i], (unsigned long long)tph[i]);
+    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_cycles[i], (unsigned long long)tph[i]);
 #endif
 
+    TC_MARK(30);
+    // every issued pass has been consumed (the exit test follows S1, before the issuing warp launches the next one)
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     if (a.counters) {
         const unsigned long long c0 = warp_sum<unsigned long long>(n_acc_warm), c1 = warp_sum<unsigned long long>(n_acc_post);
         const unsigned long long c2 = warp_sum<unsigned long long>(n_sumL), c3 = warp_sum<unsigned long long>(n_sumL2);
@@ -559,6 +716,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hmc_random_tc_kernel(const hmc_
 
 }  // namespace
 
+#ifdef HMC_TC_DEBUG
+extern "C" int hmc_debug_tc_progress(int* mapped) { volatile int* p = mapped; return (int)cudaMemcpyToSymbol(g_tc_dbg, &p, sizeof(p)); }
+#endif
+
 #ifdef HMC_PROFILE_PHASES
 extern "C" int hmc_debug_tc_cycles(unsigned long long* out8, int reset) {
     if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)); return 0; }
@@ -567,10 +728,11 @@ extern "C" int hmc_debug_tc_cycles(unsigned long long* out8, int reset) {
 }
 #endif
 
-static size_t tc_smem_bytes() {
-    return 3 * (size_t)TC_APART + 3 * (size_t)TC_BPART + (size_t)TC_DCH * TC_M * 16 + sizeof(float) * (2 * TC_KP + 4 * TC_SLOTS * 128) +
-           sizeof(TcShared) + 64;
+constexpr size_t tc_smem_bytes() {
+    return 3 * (size_t)TC_BPART + sizeof(float) * (2 * TC_KP + TC_M * TC_SROW) + sizeof(TcShared) + 64;
 }
+
+static_assert(tc_smem_bytes() <= 232448, "shared memory of the tensor-core kernel exceeds 227 KB");
 
 bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
@@ -591,7 +753,7 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
     unsigned int* queue = (unsigned int*)a.state_g;
     HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
-    hmc_random_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(a, queue);
+    hmc_random_tc_kernel<<<grid, TC_NT, smem, stream>>>(a, queue);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }

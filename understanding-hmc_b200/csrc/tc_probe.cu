@@ -28,7 +28,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                                    // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
-__global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, float* __restrict__ C) {
+__global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B, float* __restrict__ C, int ts) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint4* As = reinterpret_cast<uint4*>(smem);                 // [KC][M] 16-byte chunks
     uint4* Bs = As + KC * M;                                    // [KC][N]
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restric
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;");            // generic-proxy smem writes -> visible to the tensor core
@@ -52,6 +52,21 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restric
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t ACOL = 128;                              // A operand in TMEM (ts mode): columns ACOL .. ACOL + K/2
+    if (ts) {
+        // thread t <-> row t: K bf16 values packed two per 32-bit column (low half = even k), 8 columns per tcgen05.st
+        for (int c0 = 0; c0 < K / 2; c0 += 8) {
+            uint32_t w[8];
+            for (int c = 0; c < 8; ++c) w[c] = *reinterpret_cast<const uint32_t*>(A + (size_t)tid * K + 2 * (c0 + c));
+            const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + ACOL + (uint32_t)c0;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
 
     if (tid == 0) {
         // instruction descriptor: D = F32, A = B = BF16, both K-major, N, M
@@ -61,6 +76,13 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restric
             const uint64_t da = make_desc(a0 + ks * 2 * M * 16, M * 16, 8 * 16);
             const uint64_t db = make_desc(b0 + ks * 2 * N * 16, N * 16, 8 * 16);
             const uint32_t acc = ks > 0 ? 1u : 0u;
+            if (ts) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                    ::"r"(tmem), "r"(tmem + ACOL + 8u * ks), "l"(db), "r"(idesc), "r"(acc), "r"(0u));
+                continue;
+            }
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const uint16_t* __restric
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
 int main() {
@@ -109,13 +131,17 @@ int main() {
     CK(cudaMemset(dC, 0, hC.size() * 4));
     const size_t smem = (size_t)KC * (M + N) * 16 + 64;
     CK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_probe_kernel<<<1, 128, smem>>>(dA, dB, dC);
+    for (int ts = 0; ts < 2; ++ts) {
+    CK(cudaMemset(dC, 0, hC.size() * 4));
+    tc_probe_kernel<<<1, 128, smem>>>(dA, dB, dC, ts);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(hC.data(), dC, hC.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0, maxref = 0;
     for (int i = 0; i < M * N; ++i) { maxerr = fmax(maxerr, fabs((double)hC[i] - ref[i])); maxref = fmax(maxref, fabs((double)ref[i])); }
+    printf(ts ? "A operand from TMEM (tcgen05.st): " : "A operand from shared memory: ");
     printf("tcgen05 probe: max |C - ref| = %.3e (max |ref| = %.3f)  C[0][0..3] = %f %f %f %f  ref = %f %f %f %f\n", maxerr, maxref,
            hC[0], hC[1], hC[2], hC[3], ref[0], ref[1], ref[2], ref[3]);
     printf(maxerr < 1e-3 * maxref ? "PASS\n" : "FAIL\n");
+    }
     return 0;
 }
