@@ -49,8 +49,13 @@ e0.record()
 run["args"].iter_begin, run["args"].iter_end = IB, 2 * IB
 L.check(lib.hmc_random_run(run["args"], L.current_stream_ptr()))
 e1.record(); torch.cuda.synchronize()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 16)()
 lib.hmc_debug_tc_cycles(out, 0)
-v = np.array(list(out), dtype=float); steps = v[5]
-print("tensor-core kernel (128 chains/CTA, 4 threads per chain): %.2f ms; warp-passes %d; cycles per pass: wait for MMA %.0f, TMEM read + leapfrog update + re-split %.0f, sync + bookkeeping + sync %.0f, MMA issue (issuing warp only) %.0f, apply commands (stores / restores / new chains, take) %.0f, late momentum draws %.0f, draw-ahead (incl. group barrier) %.0f"
-      % (e0.elapsed_time(e1), steps, v[0] / steps, v[1] / steps, v[2] / steps, v[4] / (steps / 16), v[6] / steps, (v[3] - v[6]) / steps, v[7] / steps))
+v = np.array(list(out), dtype=float)
+print("tensor-core kernel (128 chains/CTA, 4 threads per chain + issuing warp): %.2f ms" % e0.elapsed_time(e1))
+for name, o, n in (("bookkeeping warps (slice 0)", 0, 4), ("other worker warps", 8, 12)):
+    steps = v[o + 5]
+    print("  %s: passes/warp %.0f; cycles per pass: apply commands %.0f, wait for MMA %.0f, TMEM read + leapfrog update + re-split + TMEM write %.0f, "
+          "S1 barrier %.0f, %s %.0f, group barrier %.0f" % (name, steps / (148 * n), v[o + 7] / steps, v[o + 0] / steps, v[o + 1] / steps, v[o + 2] / steps,
+                                                         "bookkeeping (P2)" if o == 0 else "momentum draws", v[o + 3] / steps, v[o + 6] / steps))
+print("  issuing warp: %.0f cycles per pass inside the MMA issue" % (v[4] / (v[5] / 4)))

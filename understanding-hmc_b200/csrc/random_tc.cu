@@ -40,8 +40,8 @@ __device__ volatile int* g_tc_dbg = nullptr;
 #endif
 
 #ifdef HMC_PROFILE_PHASES
-__device__ unsigned long long g_tc_cycles[8];
-#define TP_T(x) const long long x = clock64()
+__device__ unsigned long long g_tc_cycles[16];     // [0..8) bookkeeping warps, [8..16) the others; slot 4 = issuing warp
+#define TP_T(x) const unsigned int x = (unsigned int)clock()
 #define TP_ADD(i, a, b) tph[i] += (b) - (a)
 #else
 #define TP_T(x)
@@ -65,7 +65,7 @@ constexpr uint32_t TC_ACOL = 128;               // first TMEM column of the A pa
 constexpr uint32_t TC_APITCH = 64;              // TMEM columns per A part (56 used: K/2)
 constexpr int TC_SROW = TC_ND;                  // floats per momentum staging row (one row per chain)
 
-enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_REFRESH = 32, CMD_INIT0 = 64, CMD_TAKE = 128 };
+enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_STATE = 32, CMD_TAKE = 128 };
 enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,17 +201,17 @@ __device__ __noinline__ void tc_gen(const TcGen g, long m, uint64_t gid, int ite
 
 struct TcShared {                       // small per-chain arrays in shared memory
     float2 red[TC_SPL][TC_M];           // partial (d.g, p.p) per slice
-    int mode[TC_M];                     // MODE_* of the gradient being evaluated
-    int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread
+    int mode[TC_M];                     // MODE_* of the gradient in flight
+    int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread, applied at the top of the next P1
     int cm[TC_M];                       // local chain index of the chain in this slot
     int cidx[TC_M];                     // stored-sample index of the command
-    int cit[TC_M];                      // iteration whose momentum is to be drawn: set with MODE_LAST for the draw ahead
-                                        // (0 = the chain ends with this trajectory), and by the late path (new chains)
+    int req[2][TC_M];                   // momentum draw requests by pass parity: iteration (| REQ_INIT0), 0 = none
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
     int gL[TC_M];
     int galive[2][4];                   // per pass parity and group: some slot still has (or wants) a chain
-    int nleft[4];                       // per group: late momentum draws requested in this pass
 };
+
+constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
 __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     float* mu_s = reinterpret_cast<float*>(Bp + 3 * TC_BPART);  // [KP]
     float* dt_s = mu_s + KP;                                    // [KP]
     float* stage_all = dt_s + KP;                               // [128][TC_SROW] momentum staging, one row per chain
-    TcShared* sh = reinterpret_cast<TcShared*>(stage_all + TC_M * TC_SROW);
+    float* q0_s = stage_all + TC_M * TC_SROW;                   // [128][TC_SROW] shifted start position of the trajectory
+    TcShared* sh = reinterpret_cast<TcShared*>(q0_s + TC_M * TC_SROW);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sh + 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -256,9 +257,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->cit[t] = 0; sh->cm[t] = 0; }
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[0][t] = 0; sh->req[1][t] = 0; sh->cm[t] = 0; }
         if (tid < 8) sh->galive[tid >> 2][tid & 3] = 1;
-        if (tid < 4) sh->nleft[tid] = 0;
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
     float* q_chain = (float*)a.q_chain;
     float* q0g = (float*)a.state_q;
-    const double vconst = a.target.v_const;
+    const float vconst = (float)a.target.v_const;
     TcGen ga;
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
     ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
@@ -340,23 +340,22 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #pragma unroll
     for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
     // bookkeeping state of chain `chain`, used by the slice-0 thread only
-    long m = -1;                     // local chain index, -1 = no chain
+    int m = -1;                      // local chain index, -1 = no chain
     int it = 0, l = 0, L = 1;        // iteration, point index of the next gradient, trajectory length
     bool init = false;               // chain start: E_chain[.,0] still to be recorded
     bool want = (slice == 0);        // needs a (new) chain
-    bool fetch = false;              // momentum of iteration `it` was requested on the late path, results are in sh->g*
-    bool delayed = false;            // operand row rewritten under the running pass: first gradient one pass later
+    bool delayed = false;            // operand row (re)written by the pending command: first gradient one pass later
+    bool need_take = false;          // new chain: its first momentum is drawn in the pass after the load
     int par = 0;                     // pass parity
-    double E_init = 0.0, E_prev = 0.0;
-    float K0 = 0.f, Knew = 0.f, lnu = 0.f;
+    float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
     uint32_t phase = 0;
     bool have_grad = false;          // a gradient pass has been issued and its accumulator is to be consumed
 #ifdef HMC_PROFILE_PHASES
-    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
-    if (slice < TC_SPL) {            // defined operand rows before the first pass: all parts zero (K padding included)
+    {                                // defined operand rows before the first pass: all parts zero (K padding included)
         put_half0(acol, x);
         put_half1(acol, x, true);    // the wide form also clears columns 12, 13 of the slice; harmless for the others
         if (wide) {                  // K padding: dims 100..111 = columns 50..55 of each part
@@ -370,11 +369,80 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
 
+    // Pass n of a worker:  P1 (apply the commands of P2(n-1), consume G(n-1))  |  S1  |  P2(n) on the slice-0 warp, momentum
+    // draws D(n) on the other three warps of the group  |  group barrier.  The issuing warp launches MMA(n) right after S1.
     TC_MARK(6);
     while (true) {
         TP_T(t0);
         TC_MARK(20);
-        // ===== P1. consume the gradient: thread-local leapfrog update of the slice (samplers.py:835-837) ==============
+        // ===== P1a. commands posted by P2 of the previous pass (visible through the group barrier) =====================
+        const int md = sh->mode[chain];
+        {
+            const int cmd = sh->cmd[chain];
+            const int nch4 = wide ? 7 : 6;
+            if (cmd) {
+                float* q0r = q0_s + chain * TC_SROW + j0;
+                if (cmd & CMD_PARK) {
+#pragma unroll
+                    for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
+                } else if (cmd & CMD_NEW) {                           // samplers.py:411-413
+                    const size_t mc = (size_t)sh->cm[chain];
+                    const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + mc * D + j0;
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) {
+                        if (c < nch4) {
+                            const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+                            if (a.iter_begin == 0) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
+                            x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
+                            x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
+                            *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                        }
+                    }
+                } else if (cmd & (CMD_STORE_Q0 | CMD_RESTORE)) {      // end of a trajectory (samplers.py:462-472)
+                    if (cmd & CMD_RESTORE) {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            if (c < nch4) {
+                                const float4 v = *reinterpret_cast<const float4*>(q0r + 4 * c);
+                                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 7; ++c)
+                            if (c < nch4) *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                    }
+                    if (cmd & (CMD_STORE_OUT | CMD_STATE)) {
+                        const size_t mc = (size_t)sh->cm[chain];
+                        float* dst = q_chain + (mc * Lc + sh->cidx[chain]) * D + j0;
+                        float* q0 = q0g + mc * D + j0;
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            if (c < nch4) {
+                                const float4 v = make_float4(x[4 * c] + mu_s[j0 + 4 * c], x[4 * c + 1] + mu_s[j0 + 4 * c + 1],
+                                                             x[4 * c + 2] + mu_s[j0 + 4 * c + 2], x[4 * c + 3] + mu_s[j0 + 4 * c + 3]);
+                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
+                                if (cmd & CMD_STATE) *reinterpret_cast<float4*>(q0 + 4 * c) = v;
+                            }
+                        }
+                    }
+                }
+                if (cmd & CMD_TAKE) {                                 // momentum drawn ahead: my slice of the chain's row
+                    const float* st = stage_all + chain * TC_SROW + j0;
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) {
+                        if (c < nch4) {
+                            const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
+                            p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        TP_T(t0b);
+        TP_ADD(7, t0, t0b);
+        // ===== P1b. consume the gradient: thread-local leapfrog update of the slice (samplers.py:835-837), re-split ======
         if (have_grad) {
             {
                 uint32_t done = 0;
@@ -387,8 +455,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             asm volatile("tcgen05.fence::after_thread_sync;");
             TC_MARK(21);
             TP_T(t1);
-            TP_ADD(0, t0, t1);
-            const int md = sh->mode[chain];
+            TP_ADD(0, t0b, t1);
             // point index of the gradient: first = half kick + drift, last = half kick only, interior = second half
             // kick of step l + first half kick of step l+1, drift
             const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -1.0f : -0.5f);
@@ -436,8 +503,13 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             }
             TP_T(t2);
             TP_ADD(1, t1, t2);
+        } else {                                                // first pass: rows of the chains loaded by nobody yet
+            put_half0(acol, x);
+            put_half1(acol, x, wide);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         TC_MARK(22);
+        TP_T(t2b);
         asm volatile("tcgen05.fence::before_thread_sync;");     // TMEM reads / writes ordered before the next MMA
         bar_all();                                              // S1: releases the issuing warp
         {
@@ -447,256 +519,141 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         have_grad = true;
         TC_MARK(23);
         TP_T(t3);
+        TP_ADD(2, t2b, t3);
 
-        // ===== P2. per-chain bookkeeping by the slice-0 thread ==========================================================
         if (slice == 0) {
-            int cmd = 0;
-            if (fetch) {                                   // the momentum requested in the previous pass has been drawn
-                Knew = 0.5f * sh->gK[chain]; L = sh->gL[chain]; lnu = sh->glnu[chain];
-                if (init) K0 = 0.5f * sh->gK0[chain];
-                n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
-                l = 0;
-                fetch = false;
-                if (a.phi_q && a.chain_id0 + m == 0 && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;   // samplers.py:444
-            }
-            const int md = sh->mode[chain];
-            if (m >= 0 && md != MODE_IDLE) {
+            // ===== P2. per-chain bookkeeping by the slice-0 thread (under the running pass) ===============================
+            int cmd = 0, req = 0;
+            const int mdp = sh->mode[chain];                    // mode of the gradient P1 has just consumed
+            if (m >= 0 && mdp != MODE_IDLE) {
                 float sv = 0.f, sk = 0.f;
 #pragma unroll
                 for (int s2 = 0; s2 < TC_SPL; ++s2) { const float2 r = sh->red[s2][chain]; sv += r.x; sk += r.y; }
                 const bool tr = a.phi_q && (a.chain_id0 + m) == 0;
-                const double V = 0.5 * (double)sv + vconst;                     // V(q) = 0.5 d.P d + const (utils.py:213-218)
-                if (md == MODE_FIRST) {
+                const float V = fmaf(0.5f, sv, vconst);                         // V(q) = 0.5 d.P d + const (utils.py:213-218)
+                if (mdp == MODE_FIRST) {
+                    // the draws of this iteration (requested at least two passes ago): samplers.py:431, 441
+                    const float Knew = 0.5f * sh->gK[chain];
+                    L = sh->gL[chain]; lnu = sh->glnu[chain];
+                    n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
+                    if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                     // samplers.py:444
                     if (init) {                                                 // samplers.py:416-420
-                        const double E0 = V + (double)K0;
-                        a.E_chain[(size_t)m * Lc] = E0;
+                        const float E0 = V + 0.5f * sh->gK0[chain];
+                        a.E_chain[(size_t)m * Lc] = (double)E0;
                         a.dE_chain[(size_t)m * Lc] = 0.0;
                         E_prev = E0;
                         init = false;
                     }
-                    E_init = V + (double)Knew;                                  // samplers.py:434-438
+                    E_init = V + Knew;                                          // samplers.py:434-438
                     if (it >= a.warm_up_num) {
                         const long idx = (it - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)m * Lc + idx] = E_init;
-                        a.dE_chain[(size_t)m * Lc + idx] = E_init - E_prev;
+                        a.E_chain[(size_t)m * Lc + idx] = (double)E_init;
+                        a.dE_chain[(size_t)m * Lc + idx] = (double)(E_init - E_prev);
                     }
                     l = 1;
                     sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
-                    if (l == L) sh->cit[chain] = (it < a.iter_end) ? it + 1 : 0;
-                } else if (md == MODE_LAST) {
+                    if (it < a.iter_end) req = it + 1;                          // next momentum: drawn during the next pass
+                } else if (mdp == MODE_LAST) {
                     // Metropolis accept (samplers.py:455-472)
-                    const double E_final = V + 0.5 * (double)sk;
-                    const double dE = E_final - E_init;
+                    const float dE = (V + 0.5f * sk) - E_init;
                     E_prev = E_init;                                            // samplers.py:460
-                    const bool accepted = (dE < 0) || ((double)lnu < -dE);      // samplers.py:462
+                    const bool accepted = (dE < 0.f) || (lnu < -dE);            // samplers.py:462
                     const bool keep = it >= a.warm_up_num;
                     if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
-                    if (keep) cmd |= CMD_STORE_OUT;
-                    sh->cidx[chain] = keep ? (int)((it - a.warm_up_num) / a.thin_rate) : 0;
+                    if (keep) { cmd |= CMD_STORE_OUT; sh->cidx[chain] = (int)((it - a.warm_up_num) / a.thin_rate); }
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
-                    if (it >= a.iter_end) {                                     // chain finished (state_q holds its position)
-                        a.state_eprev[m] = E_prev;
+                    if (it >= a.iter_end) {                                     // chain finished: its position goes to state_q
+                        a.state_eprev[m] = (double)E_prev;
+                        cmd |= CMD_STATE;
                         want = true;
-                    } else {                                                    // momentum drawn ahead, under the last pass
+                        sh->mode[chain] = MODE_IDLE;
+                    } else {
                         it += 1;
-                        Knew = 0.5f * sh->gK[chain]; L = sh->gL[chain]; lnu = sh->glnu[chain];
-                        n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
-                        l = 0;
-                        if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                 // samplers.py:444
                         cmd |= CMD_TAKE;
+                        // the pass in flight was issued from the proposal: for an accepted chain it is the first gradient
+                        // of the new trajectory, a rejected chain's row is restored in P1 and used one pass later
+                        sh->mode[chain] = accepted ? MODE_FIRST : MODE_IDLE;
+                        delayed = !accepted;
                     }
-                    // the next gradient of a continuing chain is the first point of its new trajectory.  This pass is
-                    // already running: an accepted chain's operand row is right, a rejected chain's row is rewritten
-                    // under the pass, so its first gradient is taken one pass later.
-                    if (want || !accepted) { sh->mode[chain] = MODE_IDLE; delayed = !want; }
-                    else sh->mode[chain] = MODE_FIRST;
                 } else {
                     l += 1;
-                    sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
-                    if (l == L) sh->cit[chain] = (it < a.iter_end) ? it + 1 : 0;
+                    if (l == L) sh->mode[chain] = MODE_LAST;
                 }
-            } else if (delayed) {
+            } else if (delayed) {                               // restored / loaded row: the pass in flight is its first
                 delayed = false;
                 sh->mode[chain] = MODE_FIRST;
-            }
-            if (want) {
-                // NOTE: a finished chain's STORE/RESTORE command is applied first (P3), the new chain is loaded in the
-                // next pass -- `want` stays set until then.
-                if (cmd == 0) {
-                    want = false;
-                    const unsigned int nxt = atomicAdd(queue, 1u);
-                    if (nxt < (unsigned int)a.Nchain) {
-                        m = (long)nxt;
-                        it = a.iter_begin + 1;
-                        init = (a.iter_begin == 0);
-                        if (!init) E_prev = a.state_eprev[m];
-                        if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
-                        cmd = CMD_NEW | CMD_REFRESH | (init ? CMD_INIT0 : 0);
-                        sh->cm[chain] = (int)m;
-                        sh->cit[chain] = it;
-                        fetch = true;
-                        sh->mode[chain] = MODE_IDLE;            // row loaded under the running pass
-                        delayed = true;
-                    } else {
-                        m = -1;
-                        cmd = CMD_PARK;
-                        sh->mode[chain] = MODE_IDLE;
-                    }
+                if (need_take) { cmd |= CMD_TAKE; need_take = false; }
+            } else if (want) {
+                want = false;
+                const unsigned int nxt = atomicAdd(queue, 1u);
+                if (nxt < (unsigned int)a.Nchain) {
+                    m = (int)nxt;
+                    it = a.iter_begin + 1;
+                    init = (a.iter_begin == 0);
+                    if (!init) E_prev = (float)a.state_eprev[m];
+                    if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
+                    cmd = CMD_NEW;
+                    req = it | (init ? REQ_INIT0 : 0);
+                    sh->cm[chain] = m;
+                    delayed = true;                             // row loaded in the next P1
+                    need_take = true;
+                } else {
+                    m = -1;
+                    cmd = CMD_PARK;
                 }
+                sh->mode[chain] = MODE_IDLE;
             }
             sh->cmd[chain] = cmd;
+            sh->req[par][chain] = req;
             const int alive = __any_sync(HMC_FULL_MASK, m >= 0 || want);
-            const int late = __any_sync(HMC_FULL_MASK, (cmd & CMD_REFRESH) != 0);
-            if (lane == 0) { sh->galive[par][grp] = alive; sh->nleft[grp] = late; }
-        }
-        TC_MARK(24);
-        bar_group(grp);
-        TC_MARK(25);
-        TP_T(t4a);
-        TP_ADD(2, t3, t4a);
-
-        // ===== P3. apply the commands: momentum take, sample store / restore / new chain (all four slice threads) ==========
-        {
-            const int cmd = sh->cmd[chain];
-            const int nch4 = wide ? 7 : 6;
-            if (cmd & CMD_TAKE) {                                   // momentum drawn ahead: take my slice of the chain's row
-                const float* st = stage_all + chain * TC_SROW + j0;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    if (c < nch4) {
-                        const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
-                        p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
-                    }
-                }
-            }
-            if (cmd & (CMD_STORE_Q0 | CMD_STORE_OUT | CMD_RESTORE | CMD_NEW | CMD_PARK)) {
-                const long mc = sh->cm[chain];
-                if (cmd & CMD_PARK) {
-#pragma unroll
-                    for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
-                } else if (cmd & CMD_NEW) {
-                    const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + (size_t)mc * D + j0;
-#pragma unroll
-                    for (int c = 0; c < 7; ++c) {
-                        if (c < nch4) {
-                            const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
-                            if (a.iter_begin == 0) {
-                                *reinterpret_cast<float4*>(q0g + (size_t)mc * D + j0 + 4 * c) = v;
-                                *reinterpret_cast<float4*>(q_chain + (size_t)mc * Lc * D + j0 + 4 * c) = v;     // samplers.py:413
-                            }
-                            x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
-                            x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
-                        }
-                    }
-                } else {
-                    float* dst = q_chain + ((size_t)mc * Lc + sh->cidx[chain]) * D + j0;
-                    float* q0 = q0g + (size_t)mc * D + j0;
-                    if (cmd & CMD_RESTORE) {
-#pragma unroll
-                        for (int c = 0; c < 7; ++c) {
-                            if (c < nch4) {
-                                const float4 v = *reinterpret_cast<const float4*>(q0 + 4 * c);
-                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
-                                x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
-                                x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 7; ++c) {
-                            if (c < nch4) {
-                                const float4 v = make_float4(x[4 * c] + mu_s[j0 + 4 * c], x[4 * c + 1] + mu_s[j0 + 4 * c + 1],
-                                                             x[4 * c + 2] + mu_s[j0 + 4 * c + 2], x[4 * c + 3] + mu_s[j0 + 4 * c + 3]);
-                                *reinterpret_cast<float4*>(q0 + 4 * c) = v;
-                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
-                            }
-                        }
-                    }
-                }
-            }
-            // rewritten rows -> tensor memory.  tcgen05.st is warp-wide: the other lanes rewrite their unchanged rows.
-            if (__any_sync(HMC_FULL_MASK, (cmd & (CMD_RESTORE | CMD_NEW | CMD_PARK)) != 0)) {
-                put_half0(acol, x);
-                put_half1(acol, x, wide);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            }
-            TC_MARK(26);
-            TP_T(t4b);
-            TP_ADD(6, t4a, t4b);
-
-            // ---- late momentum draws (new chains: samplers.py:415, 431): the flagged chains of the group are drawn by its
-            //      four warps in turn, then taken by the slice threads -------------------------------------------------------
-            if (sh->nleft[grp]) {
-                unsigned todo = __ballot_sync(HMC_FULL_MASK, (cmd & CMD_REFRESH) != 0);
-                int k = 0;
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    if ((k & 3) == slice) {                       // this warp draws the k-th flagged chain of its group
-                        const int cs = grp * 32 + src;
-                        const long m_s = sh->cm[cs];
-                        const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
-                        float* st = stage_all + cs * TC_SROW;
-                        float ks, ln; int Lx;
-                        if (sh->cmd[cs] & CMD_INIT0) {            // samplers.py:415: chain-start momentum, K only
-                            tc_gen(ga, m_s, gid, 0, lane, st, &ks, &Lx, &ln);
-                            if (lane == 0) sh->gK0[cs] = ks;
-                            __syncwarp();
-                        }
-                        tc_gen(ga, m_s, gid, sh->cit[cs], lane, st, &ks, &Lx, &ln);
-                        if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
-                    }
-                    ++k;
-                }
-                bar_group(grp);
-                if (cmd & CMD_REFRESH) {
-                    const float* st = stage_all + chain * TC_SROW + j0;
-#pragma unroll
-                    for (int c = 0; c < 7; ++c) {
-                        if (c < nch4) {
-                            const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
-                            p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
-                        }
-                    }
-                }
-            }
-        }
-        TC_MARK(27);
-        TP_T(t5);
-        TP_ADD(3, t4a, t5);
-
-        // ===== D. draw ahead: the next momentum of every chain whose final gradient is in flight (samplers.py:431, 441),
-        //      into the chain's own staging row; the four warps of the group share the draws ===================================
-        {
-            unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->mode[chain] == MODE_LAST && sh->cit[chain] > 0);
+            if (lane == 0) sh->galive[par][grp] = alive;
+            TP_T(t4);
+            TP_ADD(3, t3, t4);
+        } else {
+            // ===== D. momentum draws requested by P2 of the previous pass (samplers.py:415, 431, 441), into the chain's own
+            //      staging row; warp-cooperative, shared by the three non-bookkeeping warps of the group ========================
+            unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->req[par ^ 1][chain] != 0);
             int k = 0;
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                if ((k & 3) == slice) {
+                if (k == slice - 1) {
                     const int cs = grp * 32 + src;
                     const long m_s = sh->cm[cs];
+                    const int rq = sh->req[par ^ 1][cs];
+                    const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
+                    float* st = stage_all + cs * TC_SROW;
                     float ks, ln; int Lx;
-                    tc_gen(ga, m_s, (uint64_t)(a.chain_id0 + m_s), sh->cit[cs], lane, stage_all + cs * TC_SROW, &ks, &Lx, &ln);
+                    if (rq & REQ_INIT0) {                         // samplers.py:415: chain-start momentum, K only
+                        tc_gen(ga, m_s, gid, 0, lane, st, &ks, &Lx, &ln);
+                        if (lane == 0) sh->gK0[cs] = ks;
+                        __syncwarp();
+                    }
+                    tc_gen(ga, m_s, gid, rq & ~REQ_INIT0, lane, st, &ks, &Lx, &ln);
                     if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
                 }
-                ++k;
+                k = (k == 2) ? 0 : k + 1;
             }
+            TP_T(t4);
+            TP_ADD(3, t3, t4);
         }
+        TC_MARK(24);
+        TP_T(t5);
+        bar_group(grp);
+        TP_T(t6);
+        TP_ADD(6, t5, t6);
         par ^= 1;
         TC_MARK(28);
 #ifdef HMC_TC_DEBUG
         ++dbg_pass;
 #endif
-        TP_T(t6);
-        TP_ADD(7, t5, t6);
 #ifdef HMC_PROFILE_PHASES
         tph[5] += 1;
 #endif
     }
 #ifdef HMC_PROFILE_PHASES
-    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_tc_cycles[i], (unsigned long long)tph[i]);
+    if (lane == 0) for (int i = 0; i < 8; ++i) if (i != 4) atomicAdd(&g_tc_cycles[(slice == 0 ? 0 : 8) + i], (unsigned long long)tph[i]);
 #endif
 
     TC_MARK(30);
@@ -721,15 +678,15 @@ extern "C" int hmc_debug_tc_progress(int* mapped) { volatile int* p = mapped; re
 #endif
 
 #ifdef HMC_PROFILE_PHASES
-extern "C" int hmc_debug_tc_cycles(unsigned long long* out8, int reset) {
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)); return 0; }
-    cudaMemcpyFromSymbol(out8, g_tc_cycles, sizeof(unsigned long long) * 8);
+extern "C" int hmc_debug_tc_cycles(unsigned long long* out16, int reset) {
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)); return 0; }
+    cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 16);
     return 0;
 }
 #endif
 
 constexpr size_t tc_smem_bytes() {
-    return 3 * (size_t)TC_BPART + sizeof(float) * (2 * TC_KP + TC_M * TC_SROW) + sizeof(TcShared) + 64;
+    return 3 * (size_t)TC_BPART + sizeof(float) * (2 * TC_KP + 2 * TC_M * TC_SROW) + sizeof(TcShared) + 64;
 }
 
 static_assert(tc_smem_bytes() <= 232448, "shared memory of the tensor-core kernel exceeds 227 KB");
