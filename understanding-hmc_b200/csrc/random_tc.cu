@@ -114,6 +114,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// predicated in-place 128-bit shared-memory load
+__device__ __forceinline__ void lds4_if(int pr, uint32_t addr, float& a, float& b, float& c, float& d) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(a), "+f"(b), "+f"(c), "+f"(d) : "r"(addr), "r"(pr) : "memory");
+}
+
 // positions x[0..16) of a slice -> the three bf16 parts, TMEM columns acol .. acol+7 of each part
 __device__ __forceinline__ void put_half0(uint32_t acol, const float* x) {
     uint32_t w1[8], w2[8], w3[8];
@@ -213,6 +219,7 @@ struct TcShared {                       // small per-chain arrays in shared memo
 
 constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
+template <bool UDT>
 __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -375,66 +382,65 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     while (true) {
         TP_T(t0);
         TC_MARK(20);
-        // ===== P1a. commands posted by P2 of the previous pass (visible through the group barrier) =====================
+        // ===== P1a. commands posted by P2 of the previous pass (visible through the group barrier).  The register
+        //       slices are only touched by predicated in-place loads (no per-path copies of the arrays): a new or parked
+        //       chain first writes its shared-memory rows, then takes them like a restored chain. =============================
         const int md = sh->mode[chain];
         {
             const int cmd = sh->cmd[chain];
             const int nch4 = wide ? 7 : 6;
-            if (cmd) {
-                float* q0r = q0_s + chain * TC_SROW + j0;
-                if (cmd & CMD_PARK) {
-#pragma unroll
-                    for (int j = 0; j < 28; ++j) { p[j] = 0.f; x[j] = 0.f; }
-                } else if (cmd & CMD_NEW) {                           // samplers.py:411-413
+            float* q0r = q0_s + chain * TC_SROW + j0;
+            float* str = stage_all + chain * TC_SROW + j0;
+            if (cmd & (CMD_NEW | CMD_PARK)) {
+                if (cmd & CMD_NEW) {                                  // samplers.py:411-413
                     const size_t mc = (size_t)sh->cm[chain];
                     const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + mc * D + j0;
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
                         if (c < nch4) {
                             const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+                            const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
                             if (a.iter_begin == 0) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
-                            x[4 * c] = v.x - mu_s[j0 + 4 * c]; x[4 * c + 1] = v.y - mu_s[j0 + 4 * c + 1];
-                            x[4 * c + 2] = v.z - mu_s[j0 + 4 * c + 2]; x[4 * c + 3] = v.w - mu_s[j0 + 4 * c + 3];
-                            *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                            *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(v.x - mu4.x, v.y - mu4.y, v.z - mu4.z, v.w - mu4.w);
                         }
                     }
-                } else if (cmd & (CMD_STORE_Q0 | CMD_RESTORE)) {      // end of a trajectory (samplers.py:462-472)
-                    if (cmd & CMD_RESTORE) {
-#pragma unroll
-                        for (int c = 0; c < 7; ++c) {
-                            if (c < nch4) {
-                                const float4 v = *reinterpret_cast<const float4*>(q0r + 4 * c);
-                                x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 7; ++c)
-                            if (c < nch4) *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-                    }
-                    if (cmd & (CMD_STORE_OUT | CMD_STATE)) {
-                        const size_t mc = (size_t)sh->cm[chain];
-                        float* dst = q_chain + (mc * Lc + sh->cidx[chain]) * D + j0;
-                        float* q0 = q0g + mc * D + j0;
-#pragma unroll
-                        for (int c = 0; c < 7; ++c) {
-                            if (c < nch4) {
-                                const float4 v = make_float4(x[4 * c] + mu_s[j0 + 4 * c], x[4 * c + 1] + mu_s[j0 + 4 * c + 1],
-                                                             x[4 * c + 2] + mu_s[j0 + 4 * c + 2], x[4 * c + 3] + mu_s[j0 + 4 * c + 3]);
-                                if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
-                                if (cmd & CMD_STATE) *reinterpret_cast<float4*>(q0 + 4 * c) = v;
-                            }
-                        }
-                    }
-                }
-                if (cmd & CMD_TAKE) {                                 // momentum drawn ahead: my slice of the chain's row
-                    const float* st = stage_all + chain * TC_SROW + j0;
+                } else {                                              // no chain left for this slot: zero rows
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
                         if (c < nch4) {
-                            const float4 v = *reinterpret_cast<const float4*>(st + 4 * c);
-                            p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+                            *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4*>(str + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+                    }
+                }
+            }
+            if (cmd & CMD_STORE_Q0) {                                 // accepted: the proposal is the new start point
+#pragma unroll
+                for (int c = 0; c < 7; ++c)
+                    if (c < nch4) *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            }
+            {
+                const int rs = (cmd & (CMD_RESTORE | CMD_NEW | CMD_PARK)) != 0, tk = (cmd & (CMD_TAKE | CMD_PARK)) != 0;
+                const uint32_t qa = smem_u32(q0r), sa = smem_u32(str);
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    if (c < 6 || wide) {
+                        lds4_if(rs, qa + 16 * c, x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                        lds4_if(tk, sa + 16 * c, p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                    }
+                }
+            }
+            if (cmd & (CMD_STORE_OUT | CMD_STATE)) {                  // sample store (samplers.py:462-472) / end-of-block state
+                const size_t mc = (size_t)sh->cm[chain];
+                float* dst = q_chain + (mc * Lc + sh->cidx[chain]) * D + j0;
+                float* q0 = q0g + mc * D + j0;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    if (c < nch4) {
+                        const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
+                        const float4 v = make_float4(x[4 * c] + mu4.x, x[4 * c + 1] + mu4.y, x[4 * c + 2] + mu4.z, x[4 * c + 3] + mu4.w);
+                        if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
+                        if (cmd & CMD_STATE) *reinterpret_cast<float4*>(q0 + 4 * c) = v;
                     }
                 }
             }
@@ -460,6 +466,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             // kick of step l + first half kick of step l+1, drift
             const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -1.0f : -0.5f);
             const float dwt = (md == MODE_FIRST || md == MODE_MID) ? 1.f : 0.f;
+            const float dt0 = dt_s[0], kdt = kwt * dt0, ddt = dwt * dt0;      // uniform step size (UDT)
             const bool tr = slice == 0 && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0;
             if (tr && md == MODE_FIRST) {
                 double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;      // row 0: the start point (samplers.py:445)
@@ -471,12 +478,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const float gj = __uint_as_float(gv[jj]);
-                const float dtj = dt_s[j0 + jj];
+                const float dtj = UDT ? dt0 : dt_s[j0 + jj];
                 hv = fmaf(x[jj], gj, hv);
-                const float pn = fmaf(gj, kwt * dtj, p[jj]);
+                const float pn = fmaf(gj, UDT ? kdt : kwt * dtj, p[jj]);
                 hk = fmaf(pn, pn, hk);
                 p[jj] = pn;
-                x[jj] = fmaf(pn, dwt * dtj, x[jj]);
+                x[jj] = fmaf(pn, UDT ? ddt : dwt * dtj, x[jj]);
             }
             put_half0(acol, x);
             tmem_ld16(tmem_row + 16u, gv);
@@ -484,12 +491,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             for (int jj = 16; jj < 28; ++jj) {
                 if (jj < 24 || wide) {
                     const float gj = __uint_as_float(gv[jj - 16]);
-                    const float dtj = dt_s[j0 + jj];
+                    const float dtj = UDT ? dt0 : dt_s[j0 + jj];
                     hv = fmaf(x[jj], gj, hv);
-                    const float pn = fmaf(gj, kwt * dtj, p[jj]);
+                    const float pn = fmaf(gj, UDT ? kdt : kwt * dtj, p[jj]);
                     hk = fmaf(pn, pn, hk);
                     p[jj] = pn;
-                    x[jj] = fmaf(pn, dwt * dtj, x[jj]);
+                    x[jj] = fmaf(pn, UDT ? ddt : dwt * dtj, x[jj]);
                 }
             }
             put_half1(acol, x, wide);
@@ -702,7 +709,8 @@ bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
 
 int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes();
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(hmc_random_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool udt = (a.flags & 1) != 0;                 // bit 0: the step size is the same for all dimensions
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(udt ? hmc_random_tc_kernel<true> : hmc_random_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     HMC_CUDA_CHECK(cudaGetDevice(&dev));
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -710,7 +718,8 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
     unsigned int* queue = (unsigned int*)a.state_g;
     HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
-    hmc_random_tc_kernel<<<grid, TC_NT, smem, stream>>>(a, queue);
+    if (udt) hmc_random_tc_kernel<true><<<grid, TC_NT, smem, stream>>>(a, queue);
+    else hmc_random_tc_kernel<false><<<grid, TC_NT, smem, stream>>>(a, queue);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }
