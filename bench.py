@@ -9,16 +9,17 @@ chains are independent units, no data-path collective).  A "step" is 
 kernel over one ITERATION BLOCK (50 HMC iterations of every chain, ~12 leapfrog steps each, every iteration
 stored: thin=1, warm-up 0).  Definitions printed with the number:
   gradient-eval = one full grad U = P (q - mu) for one chain = 2 D^2 = 20,000 flop; value counts the
-  leapfrog gradient evaluations sum(L) only (the extra evaluation after a rejected proposal and at chain
-  start is NOT counted, but is included in roofline.achieved since the kernel does execute it).
+  leapfrog gradient evaluations sum(L) only (the extra evaluation at the first point of every trajectory is
+  NOT counted, but is included in roofline.achieved since the kernel does execute it).
 
 value      : device-timed (CUDA events on the launching stream, barrier + synchronize on both sides, max over
              ranks), chain state resident in HBM.
 e2e        : the same metric through the public API (samplers.HMC_sampler.gen_sample + compute_convergence_stats)
              with q_start in pinned HOST memory (H2D inside the timed region) and the diagnostics' result read
              back to the host (D2H inside); at N>1 the Rhat/ESS moments go through the NCCL all-reduce.
-roofline   : FP32 FMA bound (not HBM, not tensor): achieved = executed gradient evals * 2 D^2 / kernel time;
-             peak = FFMA microbenchmark measured in this run on this GPU (MEASURED_PEAKS.json has no FP32 figure).
+roofline   : tensor bound: the gradient runs on tcgen05 as an FP32-grade bf16x3 product (6 MMA passes); achieved =
+             executed gradient evals * 2 D^2 / kernel time against the measured dense bf16 peak, with the executed
+             tensor flop (x7.53) and the FP32 FFMA peak measured in this run reported beside it.
 cpu_baseline / --impl reference : the oracle port of the reference sampler (oracle/hmc_oracle.py) with the
              reference's own library calls (scipy logpdf for V, np.random.multivariate_normal for p), one
              process per host core, on a bounded sample of the same workload.
@@ -214,7 +215,7 @@ def main():
     IB = args.iter_block
     Niter = (W + K) * IB
     H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random",
-                      dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="fast", seed=2026, chain_id0=id0,
+                      dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=2026, chain_id0=id0,
                       target=spec)
     run = H.prepare_random(q_start)               # allocates outputs/state, builds the C-ABI argument block
     counters = run["counters"]
@@ -245,26 +246,39 @@ def main():
     n_traj = Nc * K * IB
     n_rej = n_traj - acc_post - int(dc[0])
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(sumL), float(sumL + n_rej)], dtype=torch.float64, device=dev)
+    # the tensor-core kernel evaluates the gradient at the first point of every trajectory too: L + 1 per iteration
+    tot = torch.tensor([float(sumL), float(sumL + n_traj)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
     ms_max = float(t.item())
     value = float(tot[0].item()) / (ms_max * 1e-3)
-    executed_local = float(sumL + n_rej)
+    executed_local = float(sumL + n_traj)
 
-    # ---- FP32 roofline of the fused kernel (rank 0's kernel, its own events) -----------------------------------
+    # ---- roofline of the fused kernel (rank 0's kernel, its own events) ----------------------------------------
+    # The gradient runs on the tensor pipe as six bf16 part products (FP32-grade bf16x3 split) of a 128 x 112 x 112
+    # tile per 128 chain-evaluations: executed tensor flop = 6 * (112/100)^2 = 7.53 x the algorithmic 2 D^2.
     peak = L.C.c_double(0.0)
     L.check(lib.hmc_ffma_peak(L.C.byref(peak), 0, stream))
     flop = executed_local * 2.0 * D * D
     achieved = flop / (ms * 1e-3) / 1e12
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    roofline = {"bound": "fp32_ffma", "kernel": "hmc_random_fast_kernel<TM=4,TN=10,NDG=10,NCG=3,WARPS=12>", "achieved": achieved,
-                "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak.value / 1e12),
-                "peak_source": "FFMA microbenchmark (hmc_ffma_peak) measured in this run; nominal 2*128*%d SMs*1.965 GHz = %.1f"
-                               % (sms, 2 * 128 * sms * 1.965e9 / 1e12),
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 0.0)) or 2250.0
+    tensor_exec = achieved * 6.0 * (112.0 / D) ** 2
+    roofline = {"bound": "tensor", "kernel": "hmc_random_tc_kernel<UDT=true> (tcgen05 bf16x3, 128 chains per CTA)",
+                "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                                else "fallback: nominal dense bf16 2250"),
                 "traffic": None, "launch_ms": ms / K,
-                "note": "algorithmic flop = executed gradient evals (sum L + one per rejected proposal) * 2*D^2"}
+                "tensor_tflops_executed": tensor_exec, "frac_executed": tensor_exec / bf16_peak,
+                "fp32_ffma_peak": peak.value / 1e12, "frac_of_fp32_ffma_peak": achieved / (peak.value / 1e12),
+                "note": "achieved = algorithmic flop (executed gradient evals: sum L + one per trajectory start) * 2*D^2 / kernel time; "
+                        "an FP32-grade gradient costs 7.53 bf16 tensor flop per algorithmic flop (tensor_tflops_executed); "
+                        "fp32_ffma_peak is the FFMA microbenchmark of this run (what a CUDA-core kernel is bounded by)"}
 
     # ---- end-to-end leg through the public API, host buffers ----------------------------------------------------
     q_pinned = torch.from_numpy(q_start).pin_memory()
@@ -275,7 +289,7 @@ def main():
     ess = None
     for i in range(2 + K):
         H2 = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB, thin_rate=1, warm_up_num=0, sampler_type="Random",
-                           dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="fast", seed=77 + i,
+                           dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=77 + i,
                            chain_id0=id0, target=spec, distributed=(world > 1))
         barrier()
         t0 = time.perf_counter()

@@ -57,7 +57,8 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     int kernel = a.kernel;
     const char* why = "";
-    if (kernel == HMC_KERNEL_AUTO) kernel = hmc_random_fast_supported(a, &why) ? HMC_KERNEL_FAST : HMC_KERNEL_GENERIC;
+    if (kernel == HMC_KERNEL_AUTO)                  // tensor-core kernel where it applies, then the FFMA kernel, then the generic one
+        kernel = hmc_random_tc_supported(a, &why) ? HMC_KERNEL_TC : hmc_random_fast_supported(a, &why) ? HMC_KERNEL_FAST : HMC_KERNEL_GENERIC;
     if (kernel == HMC_KERNEL_FAST) {
         if (!hmc_random_fast_supported(a, &why)) {
             hmc_set_error("fast kernel does not cover this configuration: %s", why);
