@@ -66,7 +66,7 @@ def test_host_finishing_rule_equals_oracle():
         V = np.zeros((n, D))
         for t in range(1, n):
             V[t] = np.sum((halves[:, t:] - halves[:, :-t]) ** 2, axis=(0, 1)) / float(m * (n - t))
-        state = [dict(rho=[], t=1, done=False, started=False, sum_rho=0) for _ in range(D)]
+        state = U._NeffState(D)
         lag0 = 1
         chunk = 1 + trial % 7
         while lag0 <= n - 1:
@@ -74,7 +74,7 @@ def test_host_finishing_rule_equals_oracle():
             if U._finish_n_eff(var, [V[lag0 + k] for k in range(nl)], m, n, state):
                 break
             lag0 += nl
-        got = np.array([m * n / (1 + 2 * st["sum_rho"]) for st in state])
+        got = m * n / (1 + 2 * state.sum_rho)
         _, want = O.convergence_stats(x, 1, 0)
         np.testing.assert_allclose(got, want, rtol=1e-12)
 

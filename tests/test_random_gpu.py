@@ -246,6 +246,38 @@ def test_fast_kernel_slot_refill_matches_generic(kernel):
     np.testing.assert_allclose(F.E_chain[:, :2, 0], G.E_chain[:, :2, 0], rtol=1e-5)
 
 
+@pytest.mark.parametrize("nsb", [2, 5])
+def test_tc_kernel_sub_blocks_match_generic(nsb, monkeypatch):
+    """The tensor-core kernel's work queue hands out (chain, sub-block of the iteration block) units; a chain's units
+    may run in different CTAs and pass position / E_prev through state_q / state_eprev.  Forced here with few chains
+    (every later unit has to wait for its predecessor): same Philox draws as the generic kernel => same trajectory
+    lengths, first trajectory to rel 1e-5, same chain-0 trajectory record, matching energies and acceptance."""
+    import samplers as S
+    monkeypatch.setenv("HMC_B200_TC_SUBBLOCKS", str(nsb))
+    D, Nchain, Niter = 100, 700, 10
+    spec = S.MVNSpec.from_cov(np.linspace(-1, 1, D), O.equicorrelated_cov(D, 0.95))
+    q_start = np.random.RandomState(8).standard_normal((Nchain, D)).astype(np.float32) * 1.4
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=0.1, L_low=5,
+              L_high=20, dtype="float32", seed=3, target=spec)
+    F = S.HMC_sampler(D, None, None, kernel="tc", **kw)
+    F.gen_sample(q_start, N_save_chain0=4, verbose=False, quiet=True)
+    monkeypatch.delenv("HMC_B200_TC_SUBBLOCKS")
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, N_save_chain0=4, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L
+    np.testing.assert_array_equal(F.q_chain[:, 0], G.q_chain[:, 0])
+    amp = np.linalg.norm(q_start.astype(float), axis=1)
+    rel = np.linalg.norm(F.q_chain[:, 1] - G.q_chain[:, 1], axis=1) / amp
+    assert np.quantile(rel, 0.99) < 1e-5
+    assert np.all(np.isfinite(F.q_chain)) and np.abs(F.q_chain[:, -1]).max() < 50
+    assert abs(F.accept_R - G.accept_R) < 2e-2
+    np.testing.assert_allclose(F.E_chain[:, :2, 0], G.E_chain[:, :2, 0], rtol=1e-5)
+    # every stored energy difference is E_init(it) - E_init(it - 1) of the same chain, also across unit boundaries
+    np.testing.assert_allclose(F.dE_chain[:, 1:, 0], np.diff(F.E_chain[:, :, 0], axis=1), rtol=0, atol=2e-4)
+    assert [len(x) for x in F.phi_q] == [len(x) for x in G.phi_q]
+    np.testing.assert_allclose(F.phi_q[0], G.phi_q[0], rtol=0, atol=1e-4)
+
+
 @pytest.mark.parametrize("D,rho", [(128, 0.9), (101, 0.5), (64, 0.95), (33, 0.3), (24, 0.0)])
 def test_fast_kernel_other_dimensions_match_generic(D, rho):
     """The fused kernel's other tile shapes (20 < D <= 128; padded dimensions, per-dimension dt when D is odd):

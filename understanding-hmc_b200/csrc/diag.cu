@@ -112,6 +112,45 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
 }
 
+// Short series (n <= NMAX, all lags in one launch, lag0 = 1): every thread reads the n values of its (series, dimension)
+// ONCE, back to back (n independent coalesced loads in flight), and forms all lag sums from registers.  Same
+// arithmetic and summation order as the windowed kernel below for n <= 32.  One HBM pass over the stored samples.
+template <typename T, int NMAX>
+__global__ void __launch_bounds__(kDiagThreads) diag_variogram_small_kernel(const T* __restrict__ q, long Nchain, long n, int D,
+                                                                            long stride_chain, int spb, int nlags,
+                                                                            double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NMAX][D]
+    for (int t = threadIdx.x; t < NMAX * D; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int d = threadIdx.x % D;
+    const int sl = threadIdx.x / D;
+    double dacc[NMAX - 1];           // lag t = k + 1
+#pragma unroll
+    for (int k = 0; k < NMAX - 1; ++k) dacc[k] = 0.0;
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            T v[NMAX];
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * D] : T(0);
+#pragma unroll
+            for (int k = 0; k < NMAX - 1; ++k) {
+                T acc = T(0);
+#pragma unroll
+                for (int i = k + 1; i < NMAX; ++i) {
+                    if (i < n) { const T df = v[i] - v[i - k - 1]; acc = fma(df, df, acc); }
+                }
+                dacc[k] += (double)acc;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NMAX - 1; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], dacc[k]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+}
+
 // Lags t = lag0 + k, k < NL.  For every i the pair (x[i], x[i - lag0 - k]) contributes (x[i]-x[i-lag0-k])^2.
 // The last NL delayed values live in a register window addressed with compile-time indices (the time loop is
 // unrolled by NL); float partial sums are flushed into float64 every NL steps.
@@ -242,6 +281,17 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
     const int grid = grid_for(2 * Nchain, spb);
     const size_t smem = sizeof(double) * NL * D;
     HMC_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * nlags * D, stream));
+    if (lag0 == 1 && n <= NL) {                          // short series: one pass, values held in registers
+        if (dtype == HMC_F32) {
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_small_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            diag_variogram_small_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, nlags, out);
+        } else {
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_small_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            diag_variogram_small_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, nlags, out);
+        }
+        HMC_CUDA_CHECK(cudaGetLastError());
+        return HMC_OK;
+    }
     if (dtype == HMC_F32) {
         HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         diag_variogram_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);

@@ -30,6 +30,8 @@
 // chain from a global queue.
 #include "hmc_common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
+#include <cmath>
 
 #ifdef HMC_TC_DEBUG
 // progress markers in mapped host memory (readable while a kernel hangs): g_tc_dbg[warp] = pass * 100 + stage, block 0 only
@@ -65,7 +67,7 @@ constexpr uint32_t TC_ACOL = 128;               // first TMEM column of the A pa
 constexpr uint32_t TC_APITCH = 64;              // TMEM columns per A part (56 used: K/2)
 constexpr int TC_SROW = TC_ND;                  // floats per momentum staging row (one row per chain)
 
-enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_STATE = 32, CMD_TAKE = 128 };
+enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_STATE = 32, CMD_NEW0 = 64, CMD_TAKE = 128 };
 enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,8 +169,8 @@ struct TcGen {
 
 // Warp-cooperative momentum draw for one chain: lane sl < 25 draws the normals of dims 4*sl..4*sl+3 into `stage`,
 // lane 25 the scalars of the iteration.  Same arithmetic as hmc_normal4 / hmc_scalar_draws.
-__device__ __noinline__ void tc_gen(const TcGen g, long m, uint64_t gid, int iter, int lane, float* stage, float* sumsq,
-                                    int* L, float* lnu) {
+__device__ __forceinline__ void tc_gen(const TcGen& g, long m, uint64_t gid, int iter, int lane, float* stage, float* sumsq,
+                                       int* L, float* lnu) {
     constexpr int D = TC_ND, nslot = TC_ND / 4;
     float s = 0.f;
     int Lv = 1;
@@ -220,7 +222,7 @@ struct TcShared {                       // small per-chain arrays in shared memo
 constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
 template <bool UDT>
-__global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue) {
+__global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue, int* progress, int nsb, int SB) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* Bp = smem;                                   // 3 parts [KC][112] 16-byte chunks
@@ -353,6 +355,9 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     bool want = (slice == 0);        // needs a (new) chain
     bool delayed = false;            // operand row (re)written by the pending command: first gradient one pass later
     bool need_take = false;          // new chain: its first momentum is drawn in the pass after the load
+    int it_end = 0, sub = 0;         // last iteration and sub-block index of the unit being run
+    int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
+    bool publish = false;            // a finished unit's state still has to be announced
     int par = 0;                     // pass parity
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
@@ -394,13 +399,14 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             if (cmd & (CMD_NEW | CMD_PARK)) {
                 if (cmd & CMD_NEW) {                                  // samplers.py:411-413
                     const size_t mc = (size_t)sh->cm[chain];
-                    const float* src = ((a.iter_begin == 0) ? (const float*)a.q_start : q0g) + mc * D + j0;
+                    const bool fresh = (cmd & CMD_NEW0) != 0;           // chain start: q_start; otherwise the state another
+                    const float* src = (fresh ? (const float*)a.q_start : q0g) + mc * D + j0;       // unit / launch left in state_q
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
                         if (c < nch4) {
-                            const float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + 4 * c));
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
-                            if (a.iter_begin == 0) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
+                            if (fresh) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
                             *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(v.x - mu4.x, v.y - mu4.y, v.z - mu4.z, v.w - mu4.w);
                         }
                     }
@@ -559,7 +565,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                     l = 1;
                     sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
-                    if (it < a.iter_end) req = it + 1;                          // next momentum: drawn during the next pass
+                    if (it < it_end) req = it + 1;                              // next momentum: drawn during the next pass
                 } else if (mdp == MODE_LAST) {
                     // Metropolis accept (samplers.py:455-472)
                     const float dE = (V + 0.5f * sk) - E_init;
@@ -570,8 +576,9 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     else cmd |= CMD_RESTORE;
                     if (keep) { cmd |= CMD_STORE_OUT; sh->cidx[chain] = (int)((it - a.warm_up_num) / a.thin_rate); }
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
-                    if (it >= a.iter_end) {                                     // chain finished: its position goes to state_q
+                    if (it >= it_end) {                                         // unit finished: its position goes to state_q
                         a.state_eprev[m] = (double)E_prev;
+                        publish = true;
                         cmd |= CMD_STATE;
                         want = true;
                         sh->mode[chain] = MODE_IDLE;
@@ -592,22 +599,41 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 sh->mode[chain] = MODE_FIRST;
                 if (need_take) { cmd |= CMD_TAKE; need_take = false; }
             } else if (want) {
-                want = false;
-                const unsigned int nxt = atomicAdd(queue, 1u);
-                if (nxt < (unsigned int)a.Nchain) {
-                    m = (int)nxt;
-                    it = a.iter_begin + 1;
-                    init = (a.iter_begin == 0);
-                    if (!init) E_prev = (float)a.state_eprev[m];
-                    if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
-                    cmd = CMD_NEW;
-                    req = it | (init ? REQ_INIT0 : 0);
-                    sh->cm[chain] = m;
-                    delayed = true;                             // row loaded in the next P1
-                    need_take = true;
-                } else {
+                // The work queue hands out (chain, sub-block of the iteration block) units: unit u = chain u % Nchain,
+                // iterations iter_begin + (u / Nchain) * SB + 1 ... .  Splitting the block evens out the last wave of a
+                // launch; a chain's units pass its state through state_q / state_eprev and a progress counter.
+                if (publish) {                                  // (the workers stored state_q in the P1 before this barrier)
+                    __threadfence();
+                    reinterpret_cast<volatile int*>(progress)[m] = sub + 1;
+                    publish = false;
+                }
+                if (wait_unit == -1) {
+                    const unsigned int nxt = atomicAdd(queue, 1u);
+                    wait_unit = (nxt < (unsigned int)a.Nchain * (unsigned int)nsb) ? (int)nxt : -2;
+                }
+                if (wait_unit == -2) {
+                    want = false;
                     m = -1;
                     cmd = CMD_PARK;
+                } else {
+                    const int c = wait_unit % a.Nchain, sb = wait_unit / a.Nchain;
+                    if (sb == 0 || reinterpret_cast<volatile int*>(progress)[c] >= sb) {     // predecessor unit done?
+                        __threadfence();
+                        want = false;
+                        wait_unit = -1;
+                        m = c;
+                        sub = sb;
+                        it = a.iter_begin + sb * SB + 1;
+                        it_end = min(a.iter_end, a.iter_begin + (sb + 1) * SB);
+                        init = (a.iter_begin == 0 && sb == 0);
+                        if (!init) E_prev = (float)__ldcg(a.state_eprev + m);
+                        if (init && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
+                        cmd = CMD_NEW | (init ? CMD_NEW0 : 0);
+                        req = it | (init ? REQ_INIT0 : 0);
+                        sh->cm[chain] = m;
+                        delayed = true;                         // row loaded in the next P1
+                        need_take = true;
+                    }
                 }
                 sh->mode[chain] = MODE_IDLE;
             }
@@ -631,13 +657,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const int rq = sh->req[par ^ 1][cs];
                     const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
                     float* st = stage_all + cs * TC_SROW;
-                    float ks, ln; int Lx;
-                    if (rq & REQ_INIT0) {                         // samplers.py:415: chain-start momentum, K only
-                        tc_gen(ga, m_s, gid, 0, lane, st, &ks, &Lx, &ln);
-                        if (lane == 0) sh->gK0[cs] = ks;
-                        __syncwarp();
+                    float ks = 0.f, ln = 0.f; int Lx = 1;
+                    // a chain start also needs the momentum of iteration 0 (samplers.py:415, K only): one call site, two turns
+                    for (int turn = (rq & REQ_INIT0) ? 0 : 1; turn < 2; ++turn) {
+                        tc_gen(ga, m_s, gid, turn ? (rq & ~REQ_INIT0) : 0, lane, st, &ks, &Lx, &ln);
+                        if (turn == 0) { if (lane == 0) sh->gK0[cs] = ks; __syncwarp(); }
                     }
-                    tc_gen(ga, m_s, gid, rq & ~REQ_INIT0, lane, st, &ks, &Lx, &ln);
                     if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
                 }
                 k = (k == 2) ? 0 : k + 1;
@@ -716,10 +741,30 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (a.Nchain + TC_M - 1) / TC_M;
     if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
-    unsigned int* queue = (unsigned int*)a.state_g;
-    HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
-    if (udt) hmc_random_tc_kernel<true><<<grid, TC_NT, smem, stream>>>(a, queue);
-    else hmc_random_tc_kernel<false><<<grid, TC_NT, smem, stream>>>(a, queue);
+    // Sub-blocks: with more chains than slots the last wave of a launch leaves slots idle (65,536 chains on 18,944
+    // slots = 3.46 waves -> 4).  Splitting the iteration block into nsb units per chain makes the waves finer; each
+    // unit costs ~4 idle passes of set-up.
+    const int niter = a.iter_end - a.iter_begin;
+    const long slots = (long)grid * TC_M;
+    int nsb = 1;
+    if (a.Nchain > slots && niter >= 2) {
+        const double passes_per_iter = 0.5 * (a.L_low + a.L_high - 1) + 1.2;
+        double best = 1e30;
+        for (int n = 1; n <= 8 && n <= niter; ++n) {
+            const int sbn = (niter + n - 1) / n, ne = (niter + sbn - 1) / sbn;
+            const double w = (double)a.Nchain * ne / (double)slots;
+            const double cost = ceil(w) / w * (1.0 + 4.0 / (sbn * passes_per_iter));
+            if (cost < best - 1e-9) { best = cost; nsb = ne; }
+        }
+    }
+    if (const char* e = getenv("HMC_B200_TC_SUBBLOCKS")) { const int n = atoi(e); if (n >= 1 && n <= niter) nsb = n; }
+    const int SB = (niter + nsb - 1) / nsb;
+    nsb = (niter + SB - 1) / SB;
+    unsigned int* queue = (unsigned int*)a.state_g;             // [0] queue head, [16 .. 16 + Nchain) per-chain progress
+    int* progress = (int*)a.state_g + 16;
+    HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * (16 + (size_t)a.Nchain), stream));
+    if (udt) hmc_random_tc_kernel<true><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
+    else hmc_random_tc_kernel<false><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }

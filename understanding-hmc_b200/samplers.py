@@ -283,7 +283,7 @@ class HMC_sampler(sampler):
         f64 = torch.float64
         owns0 = self.chain_id0 == 0
         save_chain = N_save_chain0 > 0
-        self._q_dev = torch.zeros((Nc, Lc, D), dtype=tdt, device=dev)
+        self._q_dev = torch.empty((Nc, Lc, D), dtype=tdt, device=dev)     # every stored sample is written by the kernel
         self._E_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._dE_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
         self._q_host = self._E_host = self._dE_host = None

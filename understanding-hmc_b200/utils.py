@@ -77,41 +77,55 @@ def plot_cov_ellipse(ax, mus, covs, var_num1, var_num2, MoG_color="Blue", lw=2):
 # ----------------------------------------------------------------------------------------------------------
 # Convergence statistics on the GPU (utils.py:77-179)
 # ----------------------------------------------------------------------------------------------------------
-def _finish_n_eff(var, V_rows, m, n, state):
-    """The sequential truncation rule of utils.py:130-157 applied to the lags received so far.
+class _NeffState(object):
+    """Per-dimension state of the sequential truncation rule (vectorised over dimensions)."""
 
-    ``state`` holds, per dimension: rho list, t, done flag.  Returns True when every dimension is done."""
-    D = var.shape[0]
-    for i in range(D):
-        st = state[i]
-        if st["done"]:
-            continue
-        rho = st["rho"]
-        for row in V_rows:
-            rho.append(1. - row[i] / (2 * var[i]))                 # utils.py:134-135, 144
-        if not st["started"] and len(rho) >= 2:
-            st["started"] = True
-            if (rho[0] < 1e-2) or (rho[0] < 1e-2):                   # Q2: rho_t1 tested twice (utils.py:136)
-                st["sum_rho"] = 0
-                st["done"] = True
-                continue
-        if not st["started"]:
-            continue
-        t = st["t"]
-        while t < n - 2:                                            # utils.py:141-152
-            if len(rho) < t + 2:
-                break                                               # need more lags
-            if ((t % 2) == 1) and ((rho[t] + rho[t + 1]) < 0):
-                st["done"] = True
-                break
-            t += 1
-        st["t"] = t
-        if t >= n - 2:
-            st["done"] = True
-        if st["done"]:
-            s = float(np.sum(rho[:t]))                              # utils.py:154-156
-            st["sum_rho"] = 0 if s < 0 else s
-    return all(st["done"] for st in state)
+    def __init__(self, D):
+        self.rho = np.zeros((0, D))             # rho[k] = autocorrelation at lag k + 1, for the lags received so far
+        self.t = 1                              # common loop index of the dimensions still running (utils.py:141)
+        self.started = False
+        self.done = np.zeros(D, dtype=bool)
+        self.t_stop = np.zeros(D, dtype=int)    # number of leading rho terms summed (utils.py:154)
+        self.sum_rho = np.zeros(D)
+
+    def close(self, mask, t_stop):
+        """Finish the dimensions in ``mask``: sum_rho = max(0, sum(rho[:t_stop])) (utils.py:154-156)."""
+        if not np.any(mask):
+            return
+        t_stop = np.broadcast_to(t_stop, mask.shape)
+        csum = np.vstack([np.zeros((1, self.rho.shape[1])), np.cumsum(self.rho, axis=0)])
+        idx = np.nonzero(mask)[0]
+        s = csum[np.minimum(t_stop[idx], self.rho.shape[0]), idx]
+        self.sum_rho[idx] = np.where(s < 0, 0.0, s)
+        self.t_stop[idx] = t_stop[idx]
+        self.done[idx] = True
+
+
+def _finish_n_eff(var, V_rows, m, n, state):
+    """The sequential truncation rule of utils.py:130-157 applied to the lags received so far, all dimensions at once.
+
+    ``state``: a _NeffState.  Returns True when every dimension is done."""
+    st = state
+    rho_new = 1. - np.asarray(V_rows, dtype=float).reshape(len(V_rows), -1) / (2 * var)      # utils.py:134-135, 144
+    st.rho = np.vstack([st.rho, rho_new])
+    have = st.rho.shape[0]
+    if not st.started and have >= 2:
+        st.started = True
+        early = (~st.done) & ((st.rho[0] < 1e-2) | (st.rho[0] < 1e-2))       # Q2: rho_t1 tested twice (utils.py:136)
+        st.sum_rho[early] = 0
+        st.done |= early
+    if not st.started:
+        return False
+    hi = min(n - 2, have - 1)                                               # the loop needs rho[t + 1] (utils.py:141-152)
+    if hi > st.t:
+        ts = np.arange(st.t, hi)
+        cond = ((ts % 2) == 1)[:, None] & ((st.rho[ts] + st.rho[ts + 1]) < 0)
+        hit = cond.any(axis=0) & ~st.done
+        st.close(hit, ts[cond.argmax(axis=0)])
+        st.t = hi
+    if st.t >= n - 2:
+        st.close(~st.done, np.full(st.done.shape, st.t))
+    return bool(np.all(st.done))
 
 
 def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32):
@@ -138,7 +152,7 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
     var = W * (n - 1) / float(n) + B / float(n)                     # utils.py:123
     R = np.sqrt(var / W)                                            # utils.py:126
 
-    state = [dict(rho=[], t=1, done=False, started=False, sum_rho=0) for _ in range(D)]
+    state = _NeffState(D)
     lag0 = 1
     max_lag = n - 1
     while lag0 <= max_lag:
@@ -151,11 +165,8 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
         if _finish_n_eff(var, V_rows, m, n, state):
             break
         lag0 += nl
-    for st in state:        # chains too short to ever start (n < 3): use what exists
-        if not st["done"]:
-            s = float(np.sum(st["rho"][:st["t"]]))
-            st["sum_rho"] = 0 if s < 0 else s
-    n_eff = np.array([m * n / (1 + 2 * st["sum_rho"]) for st in state], dtype=float)   # utils.py:157
+    state.close(~state.done, np.full(D, state.t))        # chains too short to ever start (n < 3): use what exists
+    n_eff = m * n / (1 + 2 * state.sum_rho)                                             # utils.py:157
     return R, n_eff
 
 
