@@ -174,6 +174,11 @@ int hmc_diag_moments(int32_t dtype, const void* q, int64_t Nchain, int64_t n, in
                      double* out3xD, void* cuda_stream);
 int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
                        int32_t lag0, int32_t nlags, double* out_nlags_x_D, void* cuda_stream);
+/* Short series (n <= 32): both reductions above in ONE pass over the samples (every value is read once and kept in
+ * registers); out_lags[t - 1][D] for t in [1, nlags], nlags <= 31.  Same outputs as hmc_diag_moments followed by
+ * hmc_diag_variogram(lag0 = 1). */
+int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
+                          int32_t nlags, double* out3xD, double* out_lags, void* cuda_stream);
 
 /* Debug/test aid: the draws the kernels make for (seed, global chain id, iteration): 4*ceil(D/4) normals
  * (float32 Box-Muller widened to float64), the trajectory length and the acceptance uniform.  Lets the

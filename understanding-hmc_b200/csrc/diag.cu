@@ -112,21 +112,26 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
 }
 
+constexpr int kShortThreads = 128;   // ~170 registers per thread: small blocks keep 3 per SM, so loads and arithmetic of different blocks overlap
+
 // Short series (n <= NMAX, all lags in one launch, lag0 = 1): every thread reads the n values of its (series, dimension)
-// ONCE, back to back (n independent coalesced loads in flight), and forms all lag sums from registers.  Same
-// arithmetic and summation order as the windowed kernel below for n <= 32.  One HBM pass over the stored samples.
-template <typename T, int NMAX>
-__global__ void __launch_bounds__(kDiagThreads) diag_variogram_small_kernel(const T* __restrict__ q, long Nchain, long n, int D,
-                                                                            long stride_chain, int spb, int nlags,
-                                                                            double* __restrict__ out) {
-    extern __shared__ double sm[];   // [NMAX][D]
-    for (int t = threadIdx.x; t < NMAX * D; t += blockDim.x) sm[t] = 0.0;
+// ONCE, back to back (n independent coalesced loads in flight), and forms the moments (optional) and all lag sums from
+// registers: one HBM pass over the stored samples for the whole of utils.convergence_stats.  The loop over i branches
+// on the (warp-uniform) series length, so exactly n (n-1) / 2 difference terms are evaluated; per lag the terms are
+// added in increasing i, float partial sums as in the windowed kernel below.
+template <typename T, int NMAX, bool MOMENTS>
+__global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __restrict__ q, long Nchain, long n, int D,
+                                                                  long stride_chain, int spb, int nlags,
+                                                                  double* __restrict__ mom_out, double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NMAX + 3][D]
+    for (int t = threadIdx.x; t < (NMAX + 3) * D; t += blockDim.x) sm[t] = 0.0;
     __syncthreads();
     const int d = threadIdx.x % D;
     const int sl = threadIdx.x / D;
     double dacc[NMAX - 1];           // lag t = k + 1
 #pragma unroll
     for (int k = 0; k < NMAX - 1; ++k) dacc[k] = 0.0;
+    double s_std = 0.0, s_mean = 0.0, s_mean2 = 0.0;
     if (sl < spb) {
         const long nseries = 2 * Nchain;
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
@@ -134,21 +139,43 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_small_kernel(cons
             T v[NMAX];
 #pragma unroll
             for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * D] : T(0);
+            T acc[NMAX - 1];
 #pragma unroll
-            for (int k = 0; k < NMAX - 1; ++k) {
-                T acc = T(0);
+            for (int k = 0; k < NMAX - 1; ++k) acc[k] = T(0);
 #pragma unroll
-                for (int i = k + 1; i < NMAX; ++i) {
-                    if (i < n) { const T df = v[i] - v[i - k - 1]; acc = fma(df, df, acc); }
+            for (int i = 1; i < NMAX; ++i) {
+                if (i < n) {
+#pragma unroll
+                    for (int k = 0; k < i; ++k) { const T df = v[i] - v[i - k - 1]; acc[k] = fma(df, df, acc[k]); }
                 }
-                dacc[k] += (double)acc;
+            }
+#pragma unroll
+            for (int k = 0; k < NMAX - 1; ++k) dacc[k] += (double)acc[k];
+            if (MOMENTS) {           // per split chain mean and ddof = 1 standard deviation (utils.py:107-118)
+                const double x0 = (double)v[0];
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int i = 1; i < NMAX; ++i) {
+                    if (i < n) { const double e = (double)v[i] - x0; a += e; b += e * e; }
+                }
+                const double mean_s = a / (double)n;
+                double var = (b - (double)n * mean_s * mean_s) / (double)(n - 1);
+                if (var < 0.0) var = 0.0;
+                const double mean = mean_s + x0;
+                s_std += sqrt(var); s_mean += mean; s_mean2 += mean * mean;
             }
         }
 #pragma unroll
         for (int k = 0; k < NMAX - 1; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], dacc[k]);
+        if (MOMENTS) {
+            atomicAdd(&sm[(NMAX + 0) * D + d], s_std);
+            atomicAdd(&sm[(NMAX + 1) * D + d], s_mean);
+            atomicAdd(&sm[(NMAX + 2) * D + d], s_mean2);
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+    if (MOMENTS) for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(mom_out + t, sm[NMAX * D + t]);
 }
 
 // Lags t = lag0 + k, k < NL.  For every i the pair (x[i], x[i - lag0 - k]) contributes (x[i]-x[i-lag0-k])^2.
@@ -227,12 +254,12 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
     for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
 }
 
-int grid_for(long nseries, int spb) {
+int grid_for(long nseries, int spb, int per_sm = 8) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long want = (nseries + spb - 1) / spb;
-    long cap = (long)sms * 8;
+    long cap = (long)sms * per_sm;
     return (int)(want < cap ? want : cap);
 }
 
@@ -281,13 +308,14 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
     const int grid = grid_for(2 * Nchain, spb);
     const size_t smem = sizeof(double) * NL * D;
     HMC_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * nlags * D, stream));
-    if (lag0 == 1 && n <= NL) {                          // short series: one pass, values held in registers
+    if (lag0 == 1 && n <= NL && D <= kShortThreads) {    // short series: one pass, values held in registers
+        const size_t smem2 = sizeof(double) * (NL + 3) * D;
         if (dtype == HMC_F32) {
-            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_small_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            diag_variogram_small_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, nlags, out);
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<float, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            diag_short_kernel<float, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 6), kShortThreads, smem2, stream>>>((const float*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
         } else {
-            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_small_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            diag_variogram_small_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, nlags, out);
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<double, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            diag_short_kernel<double, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 6), kShortThreads, smem2, stream>>>((const double*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
         }
         HMC_CUDA_CHECK(cudaGetLastError());
         return HMC_OK;
@@ -298,6 +326,33 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
     } else {
         HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         diag_variogram_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);
+    }
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
+extern "C" int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
+                                     int32_t nlags, double* out3xD, double* out_lags, void* cuda_stream) {
+    constexpr int NL = 32;
+    HMC_REQUIRE(q && out3xD && out_lags, "NULL buffer");
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && n <= NL && D >= 1 && D <= kShortThreads, "need Nchain >= 1, 2 <= n <= %d, 1 <= D <= %d", NL, kShortThreads);
+    HMC_REQUIRE(nlags >= 1 && nlags < NL, "need 1 <= nlags <= %d", NL - 1);
+    HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int spb = kShortThreads / D;
+    const int grid = grid_for(2 * Nchain, spb, 6);            // 3 resident blocks per SM: two full waves
+    const size_t smem = sizeof(double) * (NL + 3) * D;
+    HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, sizeof(double) * 3 * D, stream));
+    HMC_CUDA_CHECK(cudaMemsetAsync(out_lags, 0, sizeof(double) * nlags * D, stream));
+    if (dtype == HMC_F32) {
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<float, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_short_kernel<float, NL, true><<<grid, kShortThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, nlags, out3xD, out_lags);
+    } else if (dtype == HMC_F64) {
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<double, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_short_kernel<double, NL, true><<<grid, kShortThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, nlags, out3xD, out_lags);
+    } else {
+        hmc_set_error("dtype must be HMC_F32 or HMC_F64");
+        return HMC_E_BADARG;
     }
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;

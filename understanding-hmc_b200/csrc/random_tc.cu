@@ -213,7 +213,8 @@ struct TcShared {                       // small per-chain arrays in shared memo
     int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread, applied at the top of the next P1
     int cm[TC_M];                       // local chain index of the chain in this slot
     int cidx[TC_M];                     // stored-sample index of the command
-    int req[2][TC_M];                   // momentum draw requests by pass parity: iteration (| REQ_INIT0), 0 = none
+    int req[TC_M];                      // pending momentum draw request: iteration (| REQ_INIT0), 0 = none (cleared by the drawer)
+    int drawn[TC_M];                    // iteration whose momentum is staged (row and scalars complete)
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
     int gL[TC_M];
     int galive[2][4];                   // per pass parity and group: some slot still has (or wants) a chain
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[0][t] = 0; sh->req[1][t] = 0; sh->cm[t] = 0; }
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; }
         if (tid < 8) sh->galive[tid >> 2][tid & 3] = 1;
     }
     if (tid == 0) {
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
     bool publish = false;            // a finished unit's state still has to be announced
     int par = 0;                     // pass parity
+    unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
     uint32_t phase = 0;
@@ -584,20 +586,25 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                         sh->mode[chain] = MODE_IDLE;
                     } else {
                         it += 1;
-                        cmd |= CMD_TAKE;
                         // the pass in flight was issued from the proposal: for an accepted chain it is the first gradient
-                        // of the new trajectory, a rejected chain's row is restored in P1 and used one pass later
-                        sh->mode[chain] = accepted ? MODE_FIRST : MODE_IDLE;
-                        delayed = !accepted;
+                        // of the new trajectory, a rejected chain's row is restored in P1 and used one pass later; a chain
+                        // whose next momentum is not staged yet (draws are rationed to one per warp and pass) waits for it
+                        const bool ready = sh->drawn[chain] == it;
+                        if (ready) cmd |= CMD_TAKE;
+                        need_take = !ready;
+                        delayed = !accepted || !ready;
+                        sh->mode[chain] = delayed ? MODE_IDLE : MODE_FIRST;
                     }
                 } else {
                     l += 1;
                     if (l == L) sh->mode[chain] = MODE_LAST;
                 }
             } else if (delayed) {                               // restored / loaded row: the pass in flight is its first
-                delayed = false;
-                sh->mode[chain] = MODE_FIRST;
-                if (need_take) { cmd |= CMD_TAKE; need_take = false; }
+                if (!need_take || sh->drawn[chain] == it) {
+                    delayed = false;
+                    sh->mode[chain] = MODE_FIRST;
+                    if (need_take) { cmd |= CMD_TAKE; need_take = false; }
+                }
             } else if (want) {
                 // The work queue hands out (chain, sub-block of the iteration block) units: unit u = chain u % Nchain,
                 // iterations iter_begin + (u / Nchain) * SB + 1 ... .  Splitting the block evens out the last wave of a
@@ -631,6 +638,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                         cmd = CMD_NEW | (init ? CMD_NEW0 : 0);
                         req = it | (init ? REQ_INIT0 : 0);
                         sh->cm[chain] = m;
+                        sh->drawn[chain] = -1;                  // (the slot's previous chain may have staged this iteration number)
                         delayed = true;                         // row loaded in the next P1
                         need_take = true;
                     }
@@ -638,34 +646,36 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 sh->mode[chain] = MODE_IDLE;
             }
             sh->cmd[chain] = cmd;
-            sh->req[par][chain] = req;
+            if (req) sh->req[chain] = req;
             const int alive = __any_sync(HMC_FULL_MASK, m >= 0 || want);
             if (lane == 0) sh->galive[par][grp] = alive;
             TP_T(t4);
             TP_ADD(3, t3, t4);
         } else {
-            // ===== D. momentum draws requested by P2 of the previous pass (samplers.py:415, 431, 441), into the chain's own
-            //      staging row; warp-cooperative, shared by the three non-bookkeeping warps of the group ========================
-            unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->req[par ^ 1][chain] != 0);
-            int k = 0;
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                if (k == slice - 1) {
-                    const int cs = grp * 32 + src;
-                    const long m_s = sh->cm[cs];
-                    const int rq = sh->req[par ^ 1][cs];
-                    const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
-                    float* st = stage_all + cs * TC_SROW;
-                    float ks = 0.f, ln = 0.f; int Lx = 1;
-                    // a chain start also needs the momentum of iteration 0 (samplers.py:415, K only): one call site, two turns
-                    for (int turn = (rq & REQ_INIT0) ? 0 : 1; turn < 2; ++turn) {
-                        tc_gen(ga, m_s, gid, turn ? (rq & ~REQ_INIT0) : 0, lane, st, &ks, &Lx, &ln);
-                        if (turn == 0) { if (lane == 0) sh->gK0[cs] = ks; __syncwarp(); }
-                    }
-                    if (lane == 0) { sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln; }
+            // ===== D. momentum draws (samplers.py:415, 431, 441) into the chain's own staging row, warp-cooperatively.  The
+            //      requests pending at the last group barrier (same snapshot in all warps of the group) are served lowest
+            //      chain first, ONE per warp and pass: a warp with two draws would hold the whole CTA at S1, and a draw has
+            //      several passes of slack (it is requested when its trajectory starts).  P2 hands a momentum to the workers
+            //      only once drawn[] says it is staged. ==========================================================================
+            unsigned todo = pend;
+            for (int k = 0; k < slice - 1 && todo; ++k) todo &= todo - 1;
+            if (todo) {
+                const int cs = grp * 32 + (__ffs(todo) - 1);
+                const long m_s = sh->cm[cs];
+                const int rq = sh->req[cs];
+                const uint64_t gid = (uint64_t)(a.chain_id0 + m_s);
+                float* st = stage_all + cs * TC_SROW;
+                float ks = 0.f, ln = 0.f; int Lx = 1;
+                // a chain start also needs the momentum of iteration 0 (samplers.py:415, K only): one call site, two turns
+                for (int turn = (rq & REQ_INIT0) ? 0 : 1; turn < 2; ++turn) {
+                    tc_gen(ga, m_s, gid, turn ? (rq & ~REQ_INIT0) : 0, lane, st, &ks, &Lx, &ln);
+                    if (turn == 0) { if (lane == 0) sh->gK0[cs] = ks; __syncwarp(); }
                 }
-                k = (k == 2) ? 0 : k + 1;
+                if (lane == 0) {
+                    sh->gK[cs] = ks; sh->gL[cs] = Lx; sh->glnu[cs] = ln;
+                    sh->drawn[cs] = rq & ~REQ_INIT0;
+                    sh->req[cs] = 0;
+                }
             }
             TP_T(t4);
             TP_ADD(3, t3, t4);
@@ -673,6 +683,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         TC_MARK(24);
         TP_T(t5);
         bar_group(grp);
+        pend = __ballot_sync(HMC_FULL_MASK, sh->req[chain] != 0);   // same snapshot in the four warps of the group
         TP_T(t6);
         TP_ADD(6, t5, t6);
         par ^= 1;

@@ -16,7 +16,7 @@ KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC = 0, 1, 2, 3
 KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST, "tc": KERNEL_TC}
 HMC_OK, HMC_E_BADARG, HMC_E_UNSUPPORTED, HMC_E_CUDA, HMC_E_DMAX = 0, 1, 2, 3, 4
 
-EXPORTS = ["hmc_random_run", "hmc_nuts_run", "hmc_diag_moments", "hmc_diag_variogram", "hmc_philox_draws",
+EXPORTS = ["hmc_random_run", "hmc_nuts_run", "hmc_diag_moments", "hmc_diag_variogram", "hmc_diag_short_series", "hmc_philox_draws",
            "hmc_ffma_peak", "hmc_version", "hmc_last_error_string"]
 
 
@@ -68,6 +68,9 @@ def load():
     lib.hmc_diag_moments.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_void_p,
                                      C.c_void_p]
     lib.hmc_diag_moments.restype = C.c_int
+    lib.hmc_diag_short_series.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hmc_diag_short_series.restype = C.c_int
     lib.hmc_diag_variogram.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]
     lib.hmc_diag_variogram.restype = C.c_int

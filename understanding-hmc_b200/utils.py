@@ -180,12 +180,22 @@ def _device_stats(x, n, group=None, lag_chunk=32):
     dtype = _L.HMC_F32 if x.dtype == torch.float32 else _L.HMC_F64
     stride_chain = x.stride(0)
 
+    fused = {}
+
     def moments_fn():
         mom = torch.empty((3, D), dtype=torch.float64, device=x.device)
+        if 2 <= n <= 32 and lag_chunk == 32 and D <= 128:    # short series: moments and every lag in one pass over the samples
+            buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
+            _L.check(lib.hmc_diag_short_series(dtype, _L.ptr(x), Nchain, n, D, stride_chain, max(1, n - 1), _L.ptr(mom),
+                                               _L.ptr(buf), _L.current_stream_ptr()))
+            fused["lags"] = buf
+            return mom
         _L.check(lib.hmc_diag_moments(dtype, _L.ptr(x), Nchain, n, D, stride_chain, _L.ptr(mom), _L.current_stream_ptr()))
         return mom
 
     def variogram_fn(lag0, nl):
+        if lag0 == 1 and "lags" in fused:
+            return fused.pop("lags")
         buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
         _L.check(lib.hmc_diag_variogram(dtype, _L.ptr(x), Nchain, n, D, stride_chain, lag0, nl, _L.ptr(buf),
                                         _L.current_stream_ptr()))
