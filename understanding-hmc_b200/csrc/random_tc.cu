@@ -73,7 +73,7 @@ enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // named barriers: 1..4 = the four warps of a 32-chain group, 5 = workers + issuing warp
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, %0;" ::"n"(TC_THREADS + 32) : "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, %0;" ::"n"(TC_NT) : "memory"); }
 __device__ __forceinline__ void bar_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -212,7 +212,8 @@ struct TcShared {                       // small per-chain arrays in shared memo
     int mode[TC_M];                     // MODE_* of the gradient in flight
     int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread, applied at the top of the next P1
     int cm[TC_M];                       // local chain index of the chain in this slot
-    int cidx[TC_M];                     // stored-sample index of the command
+    int out_req[2][TC_M];               // by pass parity: row copies for the copying warps: (stored-sample index + 1) | OUT_* flags, 0 = none
+    int out_m[2][TC_M];                 // local chain index of the copy
     int req[TC_M];                      // pending momentum draw request: iteration (| REQ_INIT0), 0 = none (cleared by the drawer)
     int drawn[TC_M];                    // iteration whose momentum is staged (row and scalars complete)
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
@@ -220,6 +221,7 @@ struct TcShared {                       // small per-chain arrays in shared memo
     int galive[2][4];                   // per pass parity and group: some slot still has (or wants) a chain
 };
 
+constexpr int OUT_SAMPLE = 1 << 29, OUT_STATE = 1 << 30;   // copy the chain's start-point row to q_chain[m][idx] / to state_q[m]
 constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
 template <bool UDT>
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; }
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; }
         if (tid < 8) sh->galive[tid >> 2][tid & 3] = 1;
     }
     if (tid == 0) {
@@ -338,6 +340,40 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #ifdef HMC_PROFILE_PHASES
             if (lane == 0) atomicAdd(&g_tc_cycles[4], (unsigned long long)tph4);
 #endif
+        } else {
+            // ===== the copying warps: a finished trajectory's stored sample (samplers.py:462-472) -- and, at the end of a
+            //       unit, the chain state -- is the chain's start-point row in shared memory (accepted proposal or restored
+            //       point) + mu: one coalesced 400-byte row per warp instruction, instead of 16-byte pieces from the four
+            //       slice threads.  Rows posted by P2(n-1), complete after the workers' P1(n), are copied during pass n. ==========
+            const int cw = warp - TC_THREADS / 32 - 1;          // 0..2
+            int par = 0;
+            while (true) {
+                bar_all();
+                const volatile int* ga_ = sh->galive[par ^ 1];
+                if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
+                int k = 0;
+                bool state_row = false;
+                for (int g = 0; g < 4; ++g) {
+                    unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->out_req[par ^ 1][g * 32 + lane] != 0);
+                    while (todo) {
+                        const int cs = g * 32 + __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        if (k == cw && lane < TC_ND / 4) {
+                            const int r = sh->out_req[par ^ 1][cs];
+                            const size_t mc = (size_t)sh->out_m[par ^ 1][cs];
+                            const float4 d4 = *reinterpret_cast<const float4*>(q0_s + cs * TC_SROW + 4 * lane);
+                            const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + 4 * lane);
+                            const float4 v = make_float4(d4.x + mu4.x, d4.y + mu4.y, d4.z + mu4.z, d4.w + mu4.w);
+                            if (r & OUT_SAMPLE)
+                                *reinterpret_cast<float4*>(q_chain + (mc * Lc + (size_t)((r & 0xfffffff) - 1)) * D + 4 * lane) = v;
+                            if (r & OUT_STATE) { *reinterpret_cast<float4*>(q0g + mc * D + 4 * lane) = v; state_row = true; }
+                        }
+                        k = (k == 2) ? 0 : k + 1;
+                    }
+                }
+                if (state_row) __threadfence();                 // the unit's progress flag is raised after the next S1
+                par ^= 1;
+            }
         }
         __syncthreads();
         return;
@@ -358,7 +394,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     bool need_take = false;          // new chain: its first momentum is drawn in the pass after the load
     int it_end = 0, sub = 0;         // last iteration and sub-block index of the unit being run
     int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
-    bool publish = false;            // a finished unit's state still has to be announced
+    int publish = 0;                 // passes until a finished unit's state (copied by a copying warp) is announced
     int par = 0;                     // pass parity
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
@@ -435,20 +471,6 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     if (c < 6 || wide) {
                         lds4_if(rs, qa + 16 * c, x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
                         lds4_if(tk, sa + 16 * c, p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
-                    }
-                }
-            }
-            if (cmd & (CMD_STORE_OUT | CMD_STATE)) {                  // sample store (samplers.py:462-472) / end-of-block state
-                const size_t mc = (size_t)sh->cm[chain];
-                float* dst = q_chain + (mc * Lc + sh->cidx[chain]) * D + j0;
-                float* q0 = q0g + mc * D + j0;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    if (c < nch4) {
-                        const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
-                        const float4 v = make_float4(x[4 * c] + mu4.x, x[4 * c + 1] + mu4.y, x[4 * c + 2] + mu4.z, x[4 * c + 3] + mu4.w);
-                        if (cmd & CMD_STORE_OUT) *reinterpret_cast<float4*>(dst + 4 * c) = v;
-                        if (cmd & CMD_STATE) *reinterpret_cast<float4*>(q0 + 4 * c) = v;
                     }
                 }
             }
@@ -538,7 +560,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 
         if (slice == 0) {
             // ===== P2. per-chain bookkeeping by the slice-0 thread (under the running pass) ===============================
-            int cmd = 0, req = 0;
+            int cmd = 0, req = 0, oreq = 0;
             const int mdp = sh->mode[chain];                    // mode of the gradient P1 has just consumed
             if (m >= 0 && mdp != MODE_IDLE) {
                 float sv = 0.f, sk = 0.f;
@@ -576,12 +598,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const bool keep = it >= a.warm_up_num;
                     if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
-                    if (keep) { cmd |= CMD_STORE_OUT; sh->cidx[chain] = (int)((it - a.warm_up_num) / a.thin_rate); }
+                    if (keep) oreq = ((int)((it - a.warm_up_num) / a.thin_rate) + 1) | OUT_SAMPLE;
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
                     if (it >= it_end) {                                         // unit finished: its position goes to state_q
                         a.state_eprev[m] = (double)E_prev;
-                        publish = true;
-                        cmd |= CMD_STATE;
+                        publish = 2;
+                        oreq |= OUT_STATE;
                         want = true;
                         sh->mode[chain] = MODE_IDLE;
                     } else {
@@ -609,11 +631,11 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 // The work queue hands out (chain, sub-block of the iteration block) units: unit u = chain u % Nchain,
                 // iterations iter_begin + (u / Nchain) * SB + 1 ... .  Splitting the block evens out the last wave of a
                 // launch; a chain's units pass its state through state_q / state_eprev and a progress counter.
-                if (publish) {                                  // (the workers stored state_q in the P1 before this barrier)
+                if (publish > 0 && --publish == 0) {            // (a copying warp stored state_q during the previous pass)
                     __threadfence();
                     reinterpret_cast<volatile int*>(progress)[m] = sub + 1;
-                    publish = false;
                 }
+                if (publish == 0) {                             // (while a finished unit's rows are being copied the slot waits)
                 if (wait_unit == -1) {
                     const unsigned int nxt = atomicAdd(queue, 1u);
                     wait_unit = (nxt < (unsigned int)a.Nchain * (unsigned int)nsb) ? (int)nxt : -2;
@@ -643,10 +665,13 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                         need_take = true;
                     }
                 }
+                }
                 sh->mode[chain] = MODE_IDLE;
             }
             sh->cmd[chain] = cmd;
             if (req) sh->req[chain] = req;
+            sh->out_req[par][chain] = oreq;
+            if (oreq) sh->out_m[par][chain] = m;
             const int alive = __any_sync(HMC_FULL_MASK, m >= 0 || want);
             if (lane == 0) sh->galive[par][grp] = alive;
             TP_T(t4);
