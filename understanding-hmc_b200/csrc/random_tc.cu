@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     bool need_take = false;          // new chain: its first momentum is drawn in the pass after the load
     int it_end = 0, sub = 0;         // last iteration and sub-block index of the unit being run
     int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
+    const bool thin1 = a.thin_rate == 1;
     int publish = 0;                 // passes until a finished unit's state (copied by a copying warp) is announced
     int par = 0;                     // pass parity
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                     E_init = V + Knew;                                          // samplers.py:434-438
                     if (it >= a.warm_up_num) {
-                        const long idx = (it - a.warm_up_num) / a.thin_rate;
+                        const long idx = thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate;
                         a.E_chain[(size_t)m * Lc + idx] = (double)E_init;
                         a.dE_chain[(size_t)m * Lc + idx] = (double)(E_init - E_prev);
                     }
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const bool keep = it >= a.warm_up_num;
                     if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
-                    if (keep) oreq = ((int)((it - a.warm_up_num) / a.thin_rate) + 1) | OUT_SAMPLE;
+                    if (keep) oreq = ((thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate) + 1) | OUT_SAMPLE;
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
                     if (it >= it_end) {                                         // unit finished: its position goes to state_q
                         a.state_eprev[m] = (double)E_prev;
@@ -631,8 +632,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 // The work queue hands out (chain, sub-block of the iteration block) units: unit u = chain u % Nchain,
                 // iterations iter_begin + (u / Nchain) * SB + 1 ... .  Splitting the block evens out the last wave of a
                 // launch; a chain's units pass its state through state_q / state_eprev and a progress counter.
-                if (publish > 0 && --publish == 0) {            // (a copying warp stored state_q during the previous pass)
-                    __threadfence();
+                if (publish > 0 && --publish == 0 && sub + 1 < nsb) {     // (a copying warp stored state_q during the previous
+                    __threadfence();                                      //  pass; the last unit of a chain has no successor)
                     reinterpret_cast<volatile int*>(progress)[m] = sub + 1;
                 }
                 if (publish == 0) {                             // (while a finished unit's rows are being copied the slot waits)
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 } else {
                     const int c = wait_unit % a.Nchain, sb = wait_unit / a.Nchain;
                     if (sb == 0 || reinterpret_cast<volatile int*>(progress)[c] >= sb) {     // predecessor unit done?
-                        __threadfence();
+                        if (sb > 0) __threadfence();
                         want = false;
                         wait_unit = -1;
                         m = c;
