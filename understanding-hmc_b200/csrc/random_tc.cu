@@ -2,7 +2,8 @@
 //
 // Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839).
 //
-// One CTA = 128 chains: 512 worker threads + one warp that only issues MMAs.  The gradient of all 128 chains,
+// One CTA = 128 chains: 512 worker threads + one warpgroup with the MMA-issuing warp and three copying warps.  The
+// gradient of all 128 chains,
 //       G[128 x N] = Dm[128 x K] * F[N x K]^T          (K = N = 112: D = 100 zero-padded to a multiple of 16)
 // runs on the 5th-generation tensor cores.  The shifted positions d = q - mu are split into three bf16 parts
 // (d = d1 + d2 + d3 exactly) that live in TENSOR MEMORY (A operand from TMEM, written with tcgen05.st: row = TMEM lane
@@ -17,17 +18,21 @@
 // pass is: read the slice of the gradient (tcgen05.ld), leapfrog update, re-split, tcgen05.st.  Per-chain sums
 // (d.g, p.p) are combined through shared memory by the slice-0 thread, which does the chain's bookkeeping
 // (energies, Metropolis accept on a Philox uniform, new trajectory length) and posts a command that all four slice
-// threads apply (sample store, restore, momentum take).  Every chain advances one gradient evaluation per pass;
-// iteration boundaries are per-chain events; the first point of each trajectory is a gradient-only pass,
-// so an iteration costs L + 1 evaluations.
+// threads apply at the top of the next pass (new start point / restore / take the next momentum: all through
+// per-chain rows in shared memory).  Every chain advances one gradient evaluation per pass; iteration boundaries are
+// per-chain events; the first point of each trajectory is a gradient-only pass, so an iteration costs
+// L + 1 evaluations.
 //
-// Schedule of a pass (n):   P1 consume G(n-1) | S1 | issuing warp: MMA(n)  ||  workers: P2 bookkeeping, group barrier,
-// P3 commands, D momentum draws | P1 ...   The MMA is issued from the rows as they stand after P1, so everything else
-// runs under it.  A rejected chain's row is rewritten under the running pass: its first gradient is taken one pass
-// later.  The next momentum of a chain is drawn while its LAST gradient is in flight (the draw does not depend on the
-// accept decision: samplers.py:431, 441 draw p, L, u at the top of every iteration), warp-cooperatively (one Philox
-// call per lane, same draws as every other kernel) into the chain's staging row.  Finished chains pull the next
-// chain from a global queue.
+// Schedule of pass n:   workers: P1a apply the commands of P2(n-1), P1b wait for MMA(n-1), update, re-split | S1 |
+// issuing warp: MMA(n) from the rows as they stand; under it, per 32-chain group, the slice-0 warp runs the bookkeeping
+// P2(n) while the other three warps draw momenta (D), then a group barrier.  An accepted chain's in-flight gradient is
+// the first gradient of its next trajectory; a rejected chain's row is restored in P1a and used one pass later.
+// Momenta are drawn ahead (the draw of iteration i+1 does not depend on the accept decision of iteration i:
+// samplers.py:431, 441 draw p, L, u at the top of every iteration), requested when a trajectory starts, warp-
+// cooperatively (one Philox call per lane, the same draws as every other kernel), one draw per warp and pass, into
+// the chain's staging row; P2 hands a momentum over only when drawn[] says it is there.  The copying warps write every
+// stored sample (and a unit's final state) as one coalesced 400-byte row taken from the chain's start-point row.
+// Finished slots pull the next (chain, sub-block of the iteration block) unit from a global queue.
 #include "hmc_common.cuh"
 #include <cuda_bf16.h>
 #include <cstdlib>
