@@ -278,6 +278,37 @@ def test_tc_kernel_sub_blocks_match_generic(nsb, monkeypatch):
     np.testing.assert_allclose(F.phi_q[0], G.phi_q[0], rtol=0, atol=1e-4)
 
 
+def test_tc_kernel_vector_dt_thinning_warmup_match_generic():
+    """Tensor-core kernel off the benchmark path: per-dimension dt (the non-uniform-dt instantiation), thinning and
+    warm-up (several iterations map to one stored index, the last write wins), a chain-id offset (multi-GPU shard) and
+    iteration blocks.  Same Philox draws as the generic kernel => same trajectory lengths; with identical accept
+    decisions the stored samples agree chain by chain, so the fraction of chains whose LAST stored sample agrees to
+    1e-3 must be large (float32 streams separate only after a decision flips at a near-tie)."""
+    import samplers as S
+    D, Nchain, Niter = 100, 1500, 13
+    mu = np.linspace(-2, 2, D)
+    spec = S.MVNSpec.from_cov(mu, O.equicorrelated_cov(D, 0.9))
+    q_start = (np.random.RandomState(21).standard_normal((Nchain, D)) * 1.3 + mu).astype(np.float32)
+    dt = 0.06 + 0.08 * np.arange(D) / D
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=3, warm_up_num=4, sampler_type="Random", dt=dt, L_low=3,
+              L_high=12, dtype="float32", seed=9, target=spec, chain_id0=123456)
+    F = S.HMC_sampler(D, None, None, kernel="tc", iter_block=5, **kw)
+    F.gen_sample(q_start, verbose=False, quiet=True)
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L
+    assert F.q_chain.shape == G.q_chain.shape == (Nchain, 1 + (Niter - 4) // 3, D)
+    assert abs(F.accept_R - G.accept_R) < 2e-2 and abs(F.accept_R_warm_up - G.accept_R_warm_up) < 2e-2
+    amp = np.linalg.norm(G.q_chain[:, -1] - mu, axis=1)
+    rel_last = np.linalg.norm(F.q_chain[:, -1] - G.q_chain[:, -1], axis=1) / amp
+    assert np.mean(rel_last < 1e-3) > 0.9, "only %.3f of the chains agree at the last stored sample" % np.mean(rel_last < 1e-3)
+    rel_first = np.linalg.norm(F.q_chain[:, 0] - G.q_chain[:, 0], axis=1) / amp
+    assert np.quantile(rel_first, 0.95) < 1e-4
+    same = rel_last < 1e-3
+    np.testing.assert_allclose(F.E_chain[same, :, 0], G.E_chain[same, :, 0], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(F.dE_chain[same, :, 0], G.dE_chain[same, :, 0], rtol=0, atol=5e-3)
+
+
 @pytest.mark.parametrize("D,rho", [(128, 0.9), (101, 0.5), (64, 0.95), (33, 0.3), (24, 0.0)])
 def test_fast_kernel_other_dimensions_match_generic(D, rho):
     """The fused kernel's other tile shapes (20 < D <= 128; padded dimensions, per-dimension dt when D is odd):

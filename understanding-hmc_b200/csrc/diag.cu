@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
 }
 
-constexpr int kShortThreads = 128;   // ~170 registers per thread: small blocks keep 3 per SM, so loads and arithmetic of different blocks overlap
+constexpr int kShortThreads = 128;   // small blocks: several resident per SM, so loads and arithmetic of different blocks overlap
 
 // Short series (n <= NMAX, all lags in one launch, lag0 = 1): every thread reads the n values of its (series, dimension)
 // ONCE, back to back (n independent coalesced loads in flight), and forms the moments (optional) and all lag sums from
@@ -120,7 +120,7 @@ constexpr int kShortThreads = 128;   // ~170 registers per thread: small blocks 
 // on the (warp-uniform) series length, so exactly n (n-1) / 2 difference terms are evaluated; per lag the terms are
 // added in increasing i, float partial sums as in the windowed kernel below.
 template <typename T, int NMAX, bool MOMENTS>
-__global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __restrict__ q, long Nchain, long n, int D,
+__global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* __restrict__ q, long Nchain, long n, int D,
                                                                   long stride_chain, int spb, int nlags,
                                                                   double* __restrict__ mom_out, double* __restrict__ out) {
     extern __shared__ double sm[];   // [NMAX + 3][D]
@@ -128,9 +128,12 @@ __global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __re
     __syncthreads();
     const int d = threadIdx.x % D;
     const int sl = threadIdx.x / D;
-    double dacc[NMAX - 1];           // lag t = k + 1
+    // lag t = k + 1.  The partial sums stay in the stream's own precision over the ~150 series a thread visits (a few
+    // thousand terms of like magnitude: 4e-6 relative in float32, below the float32 input's own rounding in n_eff) and
+    // are widened once; float64 accumulators here cost 62 registers and a third of the resident warps.
+    T acc[NMAX - 1];
 #pragma unroll
-    for (int k = 0; k < NMAX - 1; ++k) dacc[k] = 0.0;
+    for (int k = 0; k < NMAX - 1; ++k) acc[k] = T(0);
     double s_std = 0.0, s_mean = 0.0, s_mean2 = 0.0;
     if (sl < spb) {
         const long nseries = 2 * Nchain;
@@ -139,9 +142,6 @@ __global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __re
             T v[NMAX];
 #pragma unroll
             for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * D] : T(0);
-            T acc[NMAX - 1];
-#pragma unroll
-            for (int k = 0; k < NMAX - 1; ++k) acc[k] = T(0);
 #pragma unroll
             for (int i = 1; i < NMAX; ++i) {
                 if (i < n) {
@@ -149,8 +149,6 @@ __global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __re
                     for (int k = 0; k < i; ++k) { const T df = v[i] - v[i - k - 1]; acc[k] = fma(df, df, acc[k]); }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < NMAX - 1; ++k) dacc[k] += (double)acc[k];
             if (MOMENTS) {           // per split chain mean and ddof = 1 standard deviation (utils.py:107-118)
                 const double x0 = (double)v[0];
                 double a = 0.0, b = 0.0;
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(kShortThreads) diag_short_kernel(const T* __re
             }
         }
 #pragma unroll
-        for (int k = 0; k < NMAX - 1; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], dacc[k]);
+        for (int k = 0; k < NMAX - 1; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], (double)acc[k]);
         if (MOMENTS) {
             atomicAdd(&sm[(NMAX + 0) * D + d], s_std);
             atomicAdd(&sm[(NMAX + 1) * D + d], s_mean);
@@ -312,10 +310,10 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
         const size_t smem2 = sizeof(double) * (NL + 3) * D;
         if (dtype == HMC_F32) {
             HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<float, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            diag_short_kernel<float, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 6), kShortThreads, smem2, stream>>>((const float*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
+            diag_short_kernel<float, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 8), kShortThreads, smem2, stream>>>((const float*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
         } else {
             HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<double, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            diag_short_kernel<double, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 6), kShortThreads, smem2, stream>>>((const double*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
+            diag_short_kernel<double, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 8), kShortThreads, smem2, stream>>>((const double*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
         }
         HMC_CUDA_CHECK(cudaGetLastError());
         return HMC_OK;
@@ -340,7 +338,7 @@ extern "C" int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchai
     HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int spb = kShortThreads / D;
-    const int grid = grid_for(2 * Nchain, spb, 6);            // 3 resident blocks per SM: two full waves
+    const int grid = grid_for(2 * Nchain, spb, 8);            // 4 resident blocks per SM: two full waves
     const size_t smem = sizeof(double) * (NL + 3) * D;
     HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, sizeof(double) * 3 * D, stream));
     HMC_CUDA_CHECK(cudaMemsetAsync(out_lags, 0, sizeof(double) * nlags * D, stream));
