@@ -72,7 +72,15 @@ constexpr uint32_t TC_ACOL = 128;               // first TMEM column of the A pa
 constexpr uint32_t TC_APITCH = 64;              // TMEM columns per A part (56 used: K/2)
 constexpr int TC_SROW = TC_ND;                  // floats per momentum staging row (one row per chain)
 
-enum : int { CMD_STORE_Q0 = 1, CMD_STORE_OUT = 2, CMD_RESTORE = 4, CMD_NEW = 8, CMD_PARK = 16, CMD_STATE = 32, CMD_NEW0 = 64, CMD_TAKE = 128 };
+// commands of the bookkeeping thread to the four slice threads of its chain (applied at the top of the next pass)
+enum : int {
+    CMD_STORE_Q0 = 1,   // accepted: the proposal becomes the chain's start-point row
+    CMD_RESTORE = 4,    // rejected: positions <- start-point row
+    CMD_NEW = 8,        // load a chain (CMD_NEW0: from q_start, and record it as stored sample 0; else from state_q)
+    CMD_PARK = 16,      // no chain left for this slot: zero rows
+    CMD_NEW0 = 64,
+    CMD_TAKE = 128      // momentum <- the chain's staging row
+};
 enum : int { MODE_IDLE = 0, MODE_FIRST = 1, MODE_MID = 2, MODE_LAST = 3 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
