@@ -87,6 +87,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // named barriers: 1..4 = the four warps of a 32-chain group, 5 = workers + issuing warp
 __device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, %0;" ::"n"(TC_NT) : "memory"); }
+// the workers only ARRIVE at S1 (they never wait for each other there: what they need next is the MMA, through its mbarrier)
+__device__ __forceinline__ void bar_all_arrive() { asm volatile("bar.arrive 5, %0;" ::"n"(TC_NT) : "memory"); }
 __device__ __forceinline__ void bar_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -225,13 +227,14 @@ struct TcShared {                       // small per-chain arrays in shared memo
     int mode[TC_M];                     // MODE_* of the gradient in flight
     int cmd[TC_M];                      // CMD_* flags posted by the bookkeeping thread, applied at the top of the next P1
     int cm[TC_M];                       // local chain index of the chain in this slot
-    int out_req[2][TC_M];               // by pass parity: row copies for the copying warps: (stored-sample index + 1) | OUT_* flags, 0 = none
-    int out_m[2][TC_M];                 // local chain index of the copy
+    int out_req[4][TC_M];               // by pass number & 3: row copies for the copying warps: (stored-sample index + 1) | OUT_* flags, 0 = none
+    int out_m[4][TC_M];                 // local chain index of the copy
     int req[TC_M];                      // pending momentum draw request: iteration (| REQ_INIT0), 0 = none (cleared by the drawer)
     int drawn[TC_M];                    // iteration whose momentum is staged (row and scalars complete)
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
     int gL[TC_M];
-    int galive[2][4];                   // per pass parity and group: some slot still has (or wants) a chain
+    int galive[4][4];                   // per pass number & 3 and group: some slot still has (or wants) a chain
+    int stop;                           // set by the issuing warp when the CTA is done (the workers see it after the MMA wait)
 };
 
 constexpr int OUT_SAMPLE = 1 << 29, OUT_STATE = 1 << 30;   // copy the chain's start-point row to q_chain[m][idx] / to state_q[m]
@@ -282,8 +285,9 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
-        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; }
-        if (tid < 8) sh->galive[tid >> 2][tid & 3] = 1;
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; sh->out_req[2][t] = 0; sh->out_req[3][t] = 0; }
+        if (tid < 16) sh->galive[tid >> 2][tid & 3] = 1;
+        if (tid == 0) sh->stop = 0;
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         TC_MARK(4);
         if (warp == TC_THREADS / 32) {                        // the other three warps of the group only gave their registers
-            int par = 0;
+            int pn = 0;                                         // pass number
 #ifdef HMC_PROFILE_PHASES
             long long tph4 = 0;
 #endif
@@ -328,9 +332,17 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 bar_all();
                 TC_MARK(11);
-                const volatile int* ga_ = sh->galive[par ^ 1];
-                if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
-                par ^= 1;
+                const volatile int* ga_ = sh->galive[(pn - 1) & 3];     // posted by P2 of the previous pass
+                if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) {
+                    // done: the workers are (or will be) waiting for the pass that is not coming -- tell them and release them
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile int*>(&sh->stop) = 1;
+                        __threadfence_block();
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+                    }
+                    break;
+                }
+                ++pn;
                 if (lane == 0) {
     #ifdef HMC_PROFILE_PHASES
                     const long long ti0 = clock64();
@@ -359,21 +371,22 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             //       point) + mu: one coalesced 400-byte row per warp instruction, instead of 16-byte pieces from the four
             //       slice threads.  Rows posted by P2(n-1), complete after the workers' P1(n), are copied during pass n. ==========
             const int cw = warp - TC_THREADS / 32 - 1;          // 0..2
-            int par = 0;
+            int pn = 0;                                         // pass number
             while (true) {
                 bar_all();
-                const volatile int* ga_ = sh->galive[par ^ 1];
+                const int rp = (pn - 1) & 3;                    // ring slot of the previous pass's P2
+                const volatile int* ga_ = sh->galive[rp];
                 if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
                 int k = 0;
                 bool state_row = false;
                 for (int g = 0; g < 4; ++g) {
-                    unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->out_req[par ^ 1][g * 32 + lane] != 0);
+                    unsigned todo = __ballot_sync(HMC_FULL_MASK, sh->out_req[rp][g * 32 + lane] != 0);
                     while (todo) {
                         const int cs = g * 32 + __ffs(todo) - 1;
                         todo &= todo - 1;
                         if (k == cw && lane < TC_ND / 4) {
-                            const int r = sh->out_req[par ^ 1][cs];
-                            const size_t mc = (size_t)sh->out_m[par ^ 1][cs];
+                            const int r = sh->out_req[rp][cs];
+                            const size_t mc = (size_t)sh->out_m[rp][cs];
                             const float4 d4 = *reinterpret_cast<const float4*>(q0_s + cs * TC_SROW + 4 * lane);
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + 4 * lane);
                             const float4 v = make_float4(d4.x + mu4.x, d4.y + mu4.y, d4.z + mu4.z, d4.w + mu4.w);
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                 }
                 if (state_row) __threadfence();                 // the unit's progress flag is raised after the next S1
-                par ^= 1;
+                ++pn;
             }
         }
         __syncthreads();
@@ -409,7 +422,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
     const bool thin1 = a.thin_rate == 1;
     int publish = 0;                 // passes until a finished unit's state (copied by a copying warp) is announced
-    int par = 0;                     // pass parity
+    int pn = 0;                      // pass number
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
     unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
@@ -503,6 +516,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 phase ^= 1u;
             }
             asm volatile("tcgen05.fence::after_thread_sync;");
+            if (*reinterpret_cast<volatile int*>(&sh->stop)) break;    // released by the issuing warp: nothing left to do
             TC_MARK(21);
             TP_T(t1);
             TP_ADD(0, t0b, t1);
@@ -562,11 +576,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         TC_MARK(22);
         TP_T(t2b);
         asm volatile("tcgen05.fence::before_thread_sync;");     // TMEM reads / writes ordered before the next MMA
-        bar_all();                                              // S1: releases the issuing warp
-        {
-            const volatile int* ga_ = sh->galive[par ^ 1];      // written in P2 of the previous pass
-            if ((ga_[0] | ga_[1] | ga_[2] | ga_[3]) == 0) break;
-        }
+        bar_all_arrive();                                       // S1: my rows are written (the issuing warp waits for everybody)
+        bar_group(grp);                                         // the group's partial sums are in shared memory
         have_grad = true;
         TC_MARK(23);
         TP_T(t3);
@@ -684,10 +695,10 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             }
             sh->cmd[chain] = cmd;
             if (req) sh->req[chain] = req;
-            sh->out_req[par][chain] = oreq;
-            if (oreq) sh->out_m[par][chain] = m;
+            sh->out_req[pn & 3][chain] = oreq;
+            if (oreq) sh->out_m[pn & 3][chain] = m;
             const int alive = __any_sync(HMC_FULL_MASK, m >= 0 || want);
-            if (lane == 0) sh->galive[par][grp] = alive;
+            if (lane == 0) sh->galive[pn & 3][grp] = alive;
             TP_T(t4);
             TP_ADD(3, t3, t4);
         } else {
@@ -725,7 +736,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
         pend = __ballot_sync(HMC_FULL_MASK, sh->req[chain] != 0);   // same snapshot in the four warps of the group
         TP_T(t6);
         TP_ADD(6, t5, t6);
-        par ^= 1;
+        ++pn;
         TC_MARK(28);
 #ifdef HMC_TC_DEBUG
         ++dbg_pass;
