@@ -25,7 +25,9 @@
 //
 // Schedule of pass n:   workers: P1a apply the commands of P2(n-1), P1b wait for MMA(n-1), update, re-split | S1 |
 // issuing warp: MMA(n) from the rows as they stand; under it, per 32-chain group, the slice-0 warp runs the bookkeeping
-// P2(n) while the other three warps draw momenta (D), then a group barrier.  An accepted chain's in-flight gradient is
+// P2(n) while the other three warps draw momenta (D), then a group barrier.  The workers only ARRIVE at S1 (the
+// issuing and copying warps wait there): all synchronisation between workers is per 32-chain group, and what a worker
+// needs from the rest of the CTA is the MMA, which it gets through the MMA's mbarrier.  An accepted chain's in-flight gradient is
 // the first gradient of its next trajectory; a rejected chain's row is restored in P1a and used one pass later.
 // Momenta are drawn ahead (the draw of iteration i+1 does not depend on the accept decision of iteration i:
 // samplers.py:431, 441 draw p, L, u at the top of every iteration), requested when a trajectory starts, warp-
