@@ -184,7 +184,6 @@ def main():
     import torch.distributed as dist
     import hmc_b200_lib as L
     import samplers as S
-    from oracle import hmc_oracle as O   # target construction only (cov/precision); nothing timed calls it
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
@@ -204,7 +203,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cov0 = O.equicorrelated_cov(D, RHO)
+    cov0 = S.equicorrelated_cov(D, RHO)
     spec = S.MVNSpec.from_cov(np.zeros(D), cov0)
     Nc = args.chains
     id0 = rank * Nc

@@ -6,7 +6,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
 import numpy as np, torch
 import hmc_b200_lib as L, samplers as S, utils as U
-from oracle import hmc_oracle as O
 
 lib = L.load()
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
@@ -49,7 +48,7 @@ if "diag" in which:
 
 if "nuts" in which:
     D, Nc, Niter = 100, 65536, 10
-    spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+    spec = S.MVNSpec.from_cov(np.zeros(D), S.equicorrelated_cov(D, 0.95))
     q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
     for dt in (0.2, 0.1):
         H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, sampler_type="NUTS", dt=dt, d_max=10, dtype="float32",
@@ -79,7 +78,7 @@ if "case2c" in which:
 if "case3d" in which:
     # Case 3d (case3-script-2.py): D=100 rho=0.95, L in [50,200): the configuration with a meaningful ESS/sec
     D, Nc, Niter, warm = 100, 65536, 300, 100
-    spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+    spec = S.MVNSpec.from_cov(np.zeros(D), S.equicorrelated_cov(D, 0.95))
     q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
     H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, warm_up_num=warm, sampler_type="Random", dt=0.1, L_low=50,
                       L_high=200, dtype="float32", seed=3, target=spec)

@@ -5,9 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
 import numpy as np, torch
 import samplers as S, utils as U
-from oracle import hmc_oracle as O
 D, Nc, IB = 100, int(sys.argv[1]) if len(sys.argv) > 1 else 65536, int(sys.argv[2]) if len(sys.argv) > 2 else 50
-spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+spec = S.MVNSpec.from_cov(np.zeros(D), S.equicorrelated_cov(D, 0.95))
 q0 = torch.from_numpy((np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)).pin_memory()
 def sync(): torch.cuda.synchronize()
 for rep in range(4):

@@ -6,9 +6,8 @@ import numpy as np, torch
 import hmc_b200_lib as L
 L.LIB_PATH = os.path.join(ROOT, "understanding-hmc_b200", "bin", "libhmc_b200_prof.so")
 import samplers as S
-from oracle import hmc_oracle as O
 D, Nc, IB = 100, int(sys.argv[1]) if len(sys.argv) > 1 else 28416, int(sys.argv[2]) if len(sys.argv) > 2 else 20
-spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+spec = S.MVNSpec.from_cov(np.zeros(D), S.equicorrelated_cov(D, 0.95))
 q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
 lib = L.load()
 lib.hmc_debug_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]

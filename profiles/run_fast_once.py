@@ -4,9 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
 import numpy as np, torch
 import hmc_b200_lib as L, samplers as S
-from oracle import hmc_oracle as O
 D, Nc, IB, NL = 100, int(sys.argv[1]) if len(sys.argv) > 1 else 28416, int(sys.argv[2]) if len(sys.argv) > 2 else 10, 3
-spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+spec = S.MVNSpec.from_cov(np.zeros(D), S.equicorrelated_cov(D, 0.95))
 q0 = (np.random.RandomState(0).standard_normal((Nc, D)) * 1.4).astype(np.float32)
 H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB * NL, sampler_type="Random", dt=0.1, L_low=5, L_high=20,
                   dtype="float32", kernel=os.environ.get("HMC_B200_KERNEL", "fast"), seed=1, target=spec)

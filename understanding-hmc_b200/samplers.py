@@ -38,6 +38,11 @@ class MVNSpec(object):
         return cls(q0, np.linalg.inv(cov0), 0.5 * (D * np.log(2 * np.pi) + logdet))
 
 
+def equicorrelated_cov(D, rho):
+    """cov0 of the reference's drivers: (1 - rho) I + rho 1 1^T (case3-script.py:31-33)."""
+    return (1.0 - rho) * np.eye(D) + rho * np.ones((D, D))
+
+
 def extract_mvn_target(D, V, dVdq, rtol=1e-8):
     """Recover (mu, P, const) from the opaque callables by probing: g0 = dVdq(0), column i of P is
     dVdq(e_i) - g0, mu solves P mu = -g0, const = V(mu).  Verified at random points; anything that is not an
