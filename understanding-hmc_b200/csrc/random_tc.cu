@@ -218,7 +218,11 @@ __device__ __forceinline__ void tc_gen(const TcGen& g, long m, uint64_t gid, int
         Lv = __shfl_sync(HMC_FULL_MASK, Ls, nslot);
         lv = __shfl_sync(HMC_FULL_MASK, ls, nslot);
     }
-    *sumsq = warp_sum<float>(s);
+    // |p|^2 over the warp in one REDUX instead of five dependent shuffle-add rounds (the draw is a latency chain on the
+    // group's critical path): fixed point with 2^-18 resolution -- a lane's four squares stay below 2^13 (|z| < 45), 25
+    // lanes below 2^18, so the sum fits 32 bits; the rounding (4e-6 absolute on |p|^2 ~ 100) is far below the float32
+    // resolution of the energies it enters.
+    *sumsq = (float)__reduce_add_sync(HMC_FULL_MASK, __float2uint_rn(s * 262144.0f)) * (1.0f / 262144.0f);
     *L = Lv;
     *lnu = lv;
     __syncwarp();
