@@ -808,22 +808,13 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (a.Nchain + TC_M - 1) / TC_M;
     if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
-    // Sub-blocks: with more chains than slots the last wave of a launch leaves slots idle (65,536 chains on 18,944
-    // slots = 3.46 waves -> 4).  Splitting the iteration block into nsb units per chain makes the waves finer; each
-    // unit costs ~4 idle passes of set-up.
+    // Sub-blocks: the work queue can hand out (chain, sub-block of the launch's iteration block) units, which makes the
+    // last wave of a launch finer (65,536 chains on 18,944 slots = 3.46 waves).  Measured at that size: 2 sub-blocks
+    // remove 10 % of the passes but the passes of a tail are cheap and every unit costs ~8 passes of set-up and
+    // hand-off, so the launch time is the same (7.00 ms vs 7.04 ms; 3+ sub-blocks are slower).  Off by default;
+    // HMC_B200_TC_SUBBLOCKS=n turns it on (tests/test_random_gpu.py exercises the hand-off).
     const int niter = a.iter_end - a.iter_begin;
-    const long slots = (long)grid * TC_M;
     int nsb = 1;
-    if (a.Nchain > slots && niter >= 2) {
-        const double passes_per_iter = 0.5 * (a.L_low + a.L_high - 1) + 1.2;
-        double best = 1e30;
-        for (int n = 1; n <= 8 && n <= niter; ++n) {
-            const int sbn = (niter + n - 1) / n, ne = (niter + sbn - 1) / sbn;
-            const double w = (double)a.Nchain * ne / (double)slots;
-            const double cost = ceil(w) / w * (1.0 + 4.0 / (sbn * passes_per_iter));
-            if (cost < best - 1e-9) { best = cost; nsb = ne; }
-        }
-    }
     if (const char* e = getenv("HMC_B200_TC_SUBBLOCKS")) { const int n = atoi(e); if (n >= 1 && n <= niter) nsb = n; }
     const int SB = (niter + nsb - 1) / nsb;
     nsb = (niter + SB - 1) / SB;
