@@ -101,25 +101,62 @@ def cpu_reference(nchain_per_proc=8, niter=60, cores=None):
 
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """Samples clocks / throttle reasons during the timed region with one `nvidia-smi -lms 100` process
-    (the profiling recipe's clocks line)."""
+    """Samples SM clocks / clock-event (throttle) reasons DURING the timed region: an NVML polling thread (5 ms period;
+    the timed region of the default run is a few hundred ms, too short for `nvidia-smi -lms`), with the profiling
+    recipe's `nvidia-smi` line as the fallback when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.rows = []
+        self.rows = []          # [sm_mhz, max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]
+        self.thread = None
+        self.stop_flag = False
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), 2), (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), 3),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), 4), (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), 5)]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "", "", ""]
+                r = int(get_reasons(h))
+                for mask, col in bits:
+                    row[col] = "Active" if (r & mask) else "Not Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.source = "nvml, 5 ms period"
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 100"
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return
         if self.proc is None:
             return
         self.proc.terminate()
@@ -137,13 +174,13 @@ class ClockSampler(object):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
@@ -167,8 +204,10 @@ def main():
             return
         vals = []
         cores = sample = None
+        # bounded sample per step, sized so that the whole --steps/--warmup run stays within a couple of minutes
+        niter = max(12, min(60, int(60 * 23 / float(W + K))))
         for i in range(W + K):
-            v, cores, sample, _ = cpu_reference()
+            v, cores, sample, _ = cpu_reference(niter=niter)
             if i >= W:
                 vals.append(v)
         value = float(np.mean(vals))
