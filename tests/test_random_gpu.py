@@ -309,6 +309,32 @@ def test_tc_kernel_vector_dt_thinning_warmup_match_generic():
     np.testing.assert_allclose(F.dE_chain[same, :, 0], G.dE_chain[same, :, 0], rtol=0, atol=5e-3)
 
 
+def test_tc_kernel_very_short_trajectories_match_generic():
+    """L in {1, 2}: the decision of a trajectory comes one or two passes after it started, before the momentum drawn
+    ahead for the next iteration can be staged -- the chain has to wait for it (the `ready` / `need_take` path of the
+    bookkeeping), also across chain refills (more chains than one CTA's 128 slots, few iterations)."""
+    import samplers as S
+    D, Nchain, Niter = 100, 700, 15
+    spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.95))
+    q_start = (np.random.RandomState(31).standard_normal((Nchain, D)) * 1.4).astype(np.float32)
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=0.1, L_low=1,
+              L_high=3, dtype="float32", seed=17, target=spec)
+    F = S.HMC_sampler(D, None, None, kernel="tc", **kw)
+    F.gen_sample(q_start, N_save_chain0=5, verbose=False, quiet=True)
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, N_save_chain0=5, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L
+    assert [len(x) for x in F.phi_q] == [len(x) for x in G.phi_q]
+    amp = np.linalg.norm(q_start.astype(float), axis=1)
+    rel = np.linalg.norm(F.q_chain[:, 1] - G.q_chain[:, 1], axis=1) / amp
+    assert np.quantile(rel, 0.99) < 1e-5
+    rel_last = np.linalg.norm(F.q_chain[:, -1] - G.q_chain[:, -1], axis=1) / amp
+    assert np.mean(rel_last < 1e-3) > 0.9
+    assert abs(F.accept_R - G.accept_R) < 2e-2
+    np.testing.assert_allclose(F.E_chain[:, :2, 0], G.E_chain[:, :2, 0], rtol=1e-5)
+    np.testing.assert_allclose(F.dE_chain[:, 1:, 0], np.diff(F.E_chain[:, :, 0], axis=1), rtol=0, atol=2e-4)
+
+
 @pytest.mark.parametrize("D,rho", [(128, 0.9), (101, 0.5), (64, 0.95), (33, 0.3), (24, 0.0)])
 def test_fast_kernel_other_dimensions_match_generic(D, rho):
     """The fused kernel's other tile shapes (20 < D <= 128; padded dimensions, per-dimension dt when D is odd):
