@@ -41,7 +41,7 @@ enum { HMC_F32 = 0, HMC_F64 = 1 };
 
 /* which kernel implements the run */
 enum {
-    HMC_KERNEL_AUTO = 0,
+    HMC_KERNEL_AUTO = 0,    /* tensor-core kernel if it covers the run, else the FFMA2 kernel, else the generic one */
     HMC_KERNEL_GENERIC = 1, /* one warp per chain, any D <= 1024, float or double (parity workhorse) */
     HMC_KERNEL_FAST = 2,    /* FP32 FFMA2 register-tile kernel, 20 < D <= 128, identity momentum metric */
     HMC_KERNEL_TC = 3       /* tcgen05 tensor-core kernel (bf16x3 split, fp32 accumulate in TMEM), D = 100, identity metric */
