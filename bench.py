@@ -311,7 +311,10 @@ def main():
                 "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
                                 else "fallback: nominal dense bf16 2250"),
-                "traffic": None, "launch_ms": ms / K,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this workload, from the ncu
+                # --set full capture in profiles/r1j_tc_kernel_ncu_summary.csv (0.079 GB read + 1.377 GB written; the
+                # algorithmic stream of stored samples and energies is 1.36 GB)
+                "traffic": 1.455e9 if (Nc == CHAINS_PER_GPU and IB == ITER_BLOCK) else None, "launch_ms": ms / K,
                 "tensor_tflops_executed": tensor_exec, "frac_executed": tensor_exec / bf16_peak,
                 "fp32_ffma_peak": peak.value / 1e12, "frac_of_fp32_ffma_peak": achieved / (peak.value / 1e12),
                 "note": "achieved = algorithmic flop (executed gradient evals: sum L + one per trajectory start) * 2*D^2 / kernel time; "
