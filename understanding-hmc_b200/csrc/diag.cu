@@ -219,13 +219,16 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                 i0 += NL;
             }
             for (; i0 + NL <= n; i0 += NL) {        // steady state, no conditions
+                // both streams of the block are requested up front: 2 NL independent loads in flight per thread (the kernel
+                // is bound by load latency, not by HBM bandwidth: one resident block per SM at this register count)
+                T xa[NL], wn[NL];
+#pragma unroll
+                for (int r = 0; r < NL; ++r) { xa[r] = x[(i0 + r) * D]; wn[r] = x[(i0 + r - lag0) * D]; }
 #pragma unroll
                 for (int r = 0; r < NL; ++r) {
-                    const long i = i0 + r;
-                    const T xa = x[i * D];
-                    w[r] = x[(i - lag0) * D];
+                    w[r] = wn[r];
 #pragma unroll
-                    for (int k = 0; k < NL; ++k) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
+                    for (int k = 0; k < NL; ++k) { const T df = xa[r] - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
                 }
 #pragma unroll
                 for (int k = 0; k < NL; ++k) { dacc[k] += (double)acc[k]; acc[k] = T(0); }
