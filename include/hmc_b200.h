@@ -47,6 +47,15 @@ enum {
     HMC_KERNEL_TC = 3       /* tcgen05 tensor-core kernel (bf16x3 split, fp32 accumulate in TMEM), D = 100, identity metric */
 };
 
+/* hmc_random_args.flags */
+enum {
+    HMC_FLAG_UNIFORM_DT = 1, /* every entry of target.dt is equal (lets the fused kernels fold dt into constants) */
+    HMC_FLAG_TC_FP16X2 = 2   /* tensor-core kernel: the caller vouches that |q - mu| stays below ~1.6e4 and that the target's
+                                scale is not far below 1 (no component of interest under 2^-14), which lets the gradient
+                                product use the two-part fp16 split (3 tensor passes, FP32-grade) instead of the three-part
+                                bf16 split (6 passes); a trajectory that leaves the fp16 range ends in a rejection */
+};
+
 /*
  * MVN target + integrator constants, all DEVICE pointers in the compute dtype (float or double).
  * Replaces the driver closures V / dVdq (case1-script.py:39-49) and HMC_sampler.dt / inv_cov_p
@@ -84,7 +93,7 @@ typedef struct hmc_random_args {
     int32_t dtype;          /* HMC_F32 | HMC_F64 */
     int32_t kernel;         /* HMC_KERNEL_* */
     int32_t Nchain;         /* chains on this device */
-    int32_t flags;          /* bit 0: every entry of target.dt is equal (lets the fused kernel fold dt into constants) */
+    int32_t flags;          /* HMC_FLAG_* */
     int64_t chain_id0;      /* global id of local chain 0 */
     int32_t Niter;          /* total iterations of the run (samplers.py:26) */
     int32_t iter_begin;     /* iterations already done */
@@ -106,7 +115,10 @@ typedef struct hmc_random_args {
     double* E_chain;        /* [Nchain][L_chain] */
     double* dE_chain;       /* [Nchain][L_chain] */
     void* state_q;          /* [Nchain][D] compute dtype: chain position after iter_end (in: position after iter_begin) */
-    void* state_g;          /* [Nchain][D] compute dtype: scratch (force at state_q); may be NULL for the generic kernel */
+    void* state_g;          /* scratch of at least max(Nchain*D, Nchain + 64) elements of the compute dtype (work queue head, per-chain
+                               progress words; int32 word [16 + Nchain] is raised by the tensor-core kernel when HMC_FLAG_TC_FP16X2
+                               was set and a start point has |q - mu| >= 16384: repeat the run without the flag); may be NULL
+                               for the generic kernel */
     double* state_eprev;    /* [Nchain] E_previous (samplers.py:420, 460) */
     unsigned long long* counters; /* [4]: accepted during warm-up, accepted after, sum L, sum L^2 (atomically added) */
     /* chain-0 trace (only written by the device that owns global chain 0), or NULL: */
@@ -134,7 +146,10 @@ typedef struct hmc_nuts_args {
     int32_t iter_end;
     int32_t warm_up_num;
     int32_t thin_rate;
-    int32_t on_dmax;        /* 0 = "assert" (reference: the run fails, HMC_E_DMAX), 1 = "stop" (keep live point, count it) */
+    int32_t on_dmax;        /* 0 = "assert", 1 = "stop".  In both modes a chain that needs depth > d_max keeps its live point, sets
+                               bit 0 of status[] and counts in counters[3]; the call is asynchronous, so the CALLER turns
+                               counters[3] > 0 into the reference's failure (samplers.py:596-598) when on_dmax == 0 -- the Python
+                               mirror raises AssertionError; HMC_E_DMAX is the code reserved for wrappers that synchronise */
     uint64_t seed;
     hmc_target target;
     const void* q_start;
@@ -164,21 +179,57 @@ int hmc_nuts_run(const hmc_nuts_args* args, void* cuda_stream);
  * split chain 2m is samples [0,n), 2m+1 is [n,2n) of chain m.
  *
  *   hmc_diag_moments : per split chain mean and ddof=1 standard deviation (utils.py:107-118), reduced to
- *                      per-device partial sums  out[0][D] = sum_j std_j, out[1][D] = sum_j mean_j,
- *                      out[2][D] = sum_j mean_j^2  (float64) -- these are what is all-reduced across GPUs.
+ *                      per-device partial sums  out[0][D] = sum_j std_j, out[1][D] = sum_j (mean_j - c),
+ *                      out[2][D] = sum_j (mean_j - c)^2  (float64), and the shift out[3][D] = c = the first sample of
+ *                      this device's first chain: the between-chain sum of squares then does not cancel when the chains
+ *                      sit far from zero.  Devices are combined on the host from their (count, sums, shift) records
+ *                      (one all-gather; pairwise variance update).
  *   hmc_diag_variogram : out[t - lag0][D] = sum over split chains and i of (x[i+t]-x[i])^2 for
  *                      t in [lag0, lag0+nlags), nlags <= 32  (utils.py:161-179, numerator only; float64).
  * Both zero `out` first (on the stream) and then accumulate with float64 atomics.
  */
 int hmc_diag_moments(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
-                     double* out3xD, void* cuda_stream);
+                     double* out4xD, void* cuda_stream);
 int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
                        int32_t lag0, int32_t nlags, double* out_nlags_x_D, void* cuda_stream);
 /* Short series (n <= 32): both reductions above in ONE pass over the samples (every value is read once and kept in
  * registers); out_lags[t - 1][D] for t in [1, nlags], nlags <= 31.  Same outputs as hmc_diag_moments followed by
- * hmc_diag_variogram(lag0 = 1). */
+ * hmc_diag_variogram(lag0 = 1).  float32 streams with an even D take packed (two dimensions per thread, FADD2 / FFMA2)
+ * kernels; any D is accepted (dimensions are processed in tiles). */
 int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
-                          int32_t nlags, double* out3xD, double* out_lags, void* cuda_stream);
+                          int32_t nlags, double* out4xD, double* out_lags, void* cuda_stream);
+
+/*
+ * Start points on the device: replaces utils.start_pts (utils.py:204-209, np.random.multivariate_normal(q0, cov0, size)).
+ * out[m][:] = q0 + Lc z_m with z_m ~ N(0, I) from Philox keyed by (seed, chain_id0 + m), so the points do not depend on
+ * how chains are sharded.  q0 [D], Lc [D][D] (row-major lower-triangular factor, Lc Lc^T = cov0) or NULL, sd [D]
+ * (used when Lc is NULL: diagonal cov0, sd = sqrt(diag)) are float64 DEVICE arrays; out [Nchain][D] in `dtype`.
+ */
+int hmc_start_pts(int32_t dtype, uint64_t seed, int64_t chain_id0, int64_t Nchain, int32_t D, const double* q0,
+                  const double* Lc, const double* sd, void* out, void* cuda_stream);
+
+/*
+ * Sample summaries: the inputs of sampler.plot_samples (samplers.py:84-113, 160-186, 209-250) as HBM-bound reductions over
+ * the device-resident outputs, so that the host never materialises q_chain (26 GB at 65,536 chains).
+ *   hmc_summary_moments : out[0][D] = sum, out[1][D] = sum of squares over chains [0, Nchain) x samples [0, nsamp) of the
+ *                         rows at q + chain * stride_chain + sample * pitch (float64 partial sums per device).
+ *   hmc_summary_hist    : np.histogram of v = x - shift on the given bin edges (edges [nbins + 1] float64 device, ascending;
+ *                         last bin closed on the right); counts [nbins + 2]: the bins, then #below, #above.  The series is
+ *                         x[chain * stride_chain + sample * stride_sample] (a column of q_chain, or E_chain / dE_chain).
+ *   hmc_summary_select  : one pass of a radix select over the order-preserving integer keys of the series (32-bit keys for
+ *                         float32, 64-bit for float64): out[2048] += histogram of digit (key >> digit_shift) & (2^digit_bits - 1)
+ *                         over the elements with key >> prefix_shift == prefix (prefix_shift = 64: all elements).  The host walks
+ *                         the digits from the top to the k-th smallest value (np.percentile's order statistics).
+ * Counts are per device; sum them over ranks (they are plain sums) for a sharded run.
+ */
+int hmc_summary_moments(int32_t dtype, const void* q, int64_t Nchain, int64_t nsamp, int32_t D, int64_t pitch,
+                        int64_t stride_chain, double* out2xD, void* cuda_stream);
+int hmc_summary_hist(int32_t dtype, const void* x, int64_t Nchain, int64_t nsamp, int64_t stride_sample,
+                     int64_t stride_chain, double shift, const double* edges, int32_t nbins,
+                     unsigned long long* out_counts, void* cuda_stream);
+int hmc_summary_select(int32_t dtype, const void* x, int64_t Nchain, int64_t nsamp, int64_t stride_sample,
+                       int64_t stride_chain, uint64_t prefix, int32_t prefix_shift, int32_t digit_shift,
+                       int32_t digit_bits, unsigned long long* out_hist2048, void* cuda_stream);
 
 /* Debug/test aid: the draws the kernels make for (seed, global chain id, iteration): 4*ceil(D/4) normals
  * (float32 Box-Muller widened to float64), the trajectory length and the acceptance uniform.  Lets the

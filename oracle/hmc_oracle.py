@@ -147,6 +147,45 @@ def leap_frog(p_old, q_old, dt, inv_cov_p, dVdq):
     return p_new, q_new
 
 
+def leap_frog_batch(p_old, q_old, dt, inv_cov_p, tgt):
+    """``leap_frog`` (samplers.py:831-839) applied to every row of p_old / q_old at once (same statements, same order;
+    rows are independent chains).  ``tgt``: MVNTarget.  Checked against the row-by-row form in tests/test_oracle_golden.py."""
+    def dVdq(q):                                                            # case1-script.py:45-49, row-wise
+        return np.dot(q - tgt.q0, tgt.inv_cov0.T)
+    p_half = p_old - dt * np.dot(dVdq(q_old), inv_cov_p.T) / 2.
+    q_new = q_old + dt * p_half
+    p_new = p_half - dt * np.dot(dVdq(q_new), inv_cov_p.T) / 2.
+    return p_new, q_new
+
+
+def one_iteration_batch(tgt, q_init, p, L, u, dt, cov_p=None):
+    """One iteration of ``gen_sample_random`` (samplers.py:428-472) for B independent (start point, momentum, length,
+    uniform) tuples: returns dict(q_prop, p_prop, E_init, dE, decision).  Rows with L[b] < max(L) stop early."""
+    q_init = np.asarray(q_init, dtype=float)
+    B, D = q_init.shape
+    cov_p = np.diag(np.ones(D)) if cov_p is None else np.asarray(cov_p, dtype=float)
+    inv_cov_p = np.linalg.inv(cov_p)
+
+    def E(q, pp):                                                           # samplers.py:819-823, row-wise
+        d = q - tgt.q0
+        return 0.5 * np.einsum("bi,bi->b", d, np.dot(d, tgt.inv_cov0.T)) + tgt.const + \
+            0.5 * np.einsum("bi,bi->b", pp, np.dot(pp, inv_cov_p.T))
+    q = q_init.copy()
+    pp = np.asarray(p, dtype=float).copy()
+    L = np.asarray(L).astype(int)
+    E_init = E(q, pp)
+    for l in range(1, int(L.max()) + 1):                                    # samplers.py:448-449
+        on = L >= l
+        pn, qn = leap_frog_batch(pp[on], q[on], dt, inv_cov_p, tgt)
+        pp[on] = pn
+        q[on] = qn
+    dE = E(q, pp) - E_init                                                  # samplers.py:455-459
+    with np.errstate(divide="ignore"):
+        lnu = np.log(np.asarray(u, dtype=float))                            # samplers.py:461
+    decision = ((dE < 0) | (lnu < -dE)).astype(np.int32)                    # samplers.py:462
+    return dict(q_prop=q, p_prop=pp, E_init=E_init, dE=dE, decision=decision)
+
+
 class Result(object):
     """Plain attribute bag mirroring the sampler attributes (samplers.py:31-50, 359-360)."""
     pass

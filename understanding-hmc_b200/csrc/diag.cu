@@ -5,6 +5,7 @@
 // dimensions, so every load of a warp is one contiguous row segment.  Per-thread partials are float64,
 // combined per block in shared memory and added to the output with one float64 atomic per (block, value).
 #include "hmc_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -13,32 +14,37 @@ constexpr int kDiagThreads = 256;
 // `q` points at sample 0 of chain 0; `stride_chain` elements between chains; a split chain s = 2*m + h is
 // samples [h*n, h*n + n) of chain m (utils.py:102-104).
 template <typename T>
-__global__ void __launch_bounds__(kDiagThreads) diag_moments_kernel(const T* __restrict__ q, long Nchain, long n, int D,
-                                                                    long stride_chain, int spb, double* __restrict__ out) {
+__global__ void __launch_bounds__(kDiagThreads) diag_moments_kernel(const T* __restrict__ q, long Nchain, long n, int Dfull, long pitch,
+                                                                    long stride_chain, int d0, int D, int spb, double* __restrict__ out) {
+    // (D = dimensions of this tile, first dimension d0; `pitch` elements between consecutive samples)
     extern __shared__ double sm[];   // [3][D]
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) sm[t] = 0.0;
     __syncthreads();
     const int d = threadIdx.x % D;
     const int sl = threadIdx.x / D;
     double s_std = 0.0, s_mean = 0.0, s_mean2 = 0.0;
+    // chain means are accumulated relative to the first sample of this device's first chain (row 3 of `out`): sum mean^2 -
+    // m mean^2 then does not cancel when the chains sit far from zero; the host combines devices with their own shifts
+    const double cshift = (double)q[d0 + d];
+    if (blockIdx.x == 0 && sl == 0) out[3 * Dfull + d0 + d] = cshift;
     if (sl < spb) {
         const long nseries = 2 * Nchain;
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
-            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0 + d;
             const double x0 = (double)x[0];
             double a = 0.0, b = 0.0;
             long i = 0;
             for (; i + 4 <= n; i += 4) {
-                const double v0 = (double)x[(i + 0) * D] - x0, v1 = (double)x[(i + 1) * D] - x0;
-                const double v2 = (double)x[(i + 2) * D] - x0, v3 = (double)x[(i + 3) * D] - x0;
+                const double v0 = (double)x[(i + 0) * pitch] - x0, v1 = (double)x[(i + 1) * pitch] - x0;
+                const double v2 = (double)x[(i + 2) * pitch] - x0, v3 = (double)x[(i + 3) * pitch] - x0;
                 a += (v0 + v1) + (v2 + v3);
                 b += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
             }
-            for (; i < n; ++i) { const double v = (double)x[i * D] - x0; a += v; b += v * v; }
+            for (; i < n; ++i) { const double v = (double)x[i * pitch] - x0; a += v; b += v * v; }
             const double mean_s = a / (double)n;
             double var = (b - (double)n * mean_s * mean_s) / (double)(n - 1);   // ddof = 1 (utils.py:111)
             if (var < 0.0) var = 0.0;
-            const double mean = mean_s + x0;
+            const double mean = mean_s + (x0 - cshift);
             s_std += sqrt(var);
             s_mean += mean;
             s_mean2 += mean * mean;
@@ -48,13 +54,13 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_kernel(const T* __r
         atomicAdd(&sm[2 * D + d], s_mean2);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+    for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(out + (t / D) * Dfull + d0 + (t % D), sm[t]);
 }
 
 
 // float32 stream, D % 4 == 0: one thread owns FOUR adjacent dimensions of one split chain and walks the time axis
 // with 128-bit loads (8 rows in flight per thread), so that enough bytes are in flight to saturate HBM.
-__global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const float* __restrict__ q, long Nchain, long n, int D,
+__global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
                                                                           long stride_chain, int spb, double* __restrict__ out) {
     extern __shared__ double sm[];   // [3][D]
     for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) sm[t] = 0.0;
@@ -63,10 +69,15 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
     const int dq = threadIdx.x % D4;
     const int sl = threadIdx.x / D4;
     double s_std[4] = {0, 0, 0, 0}, s_mean[4] = {0, 0, 0, 0}, s_mean2[4] = {0, 0, 0, 0};
+    double cshift[4] = {0, 0, 0, 0};             // see diag_moments_kernel
     if (sl < spb) {
+        const float4 c4 = reinterpret_cast<const float4*>(q)[dq];
+        cshift[0] = c4.x; cshift[1] = c4.y; cshift[2] = c4.z; cshift[3] = c4.w;
+        if (blockIdx.x == 0 && sl == 0) { for (int c = 0; c < 4; ++c) out[3 * D + 4 * dq + c] = cshift[c]; }
         const long nseries = 2 * Nchain;
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
-            const float4* x = reinterpret_cast<const float4*>(q + (s >> 1) * stride_chain + (s & 1) * n * D) + dq;
+            const float4* x = reinterpret_cast<const float4*>(q + (s >> 1) * stride_chain + (s & 1) * n * pitch) + dq;
+            const long P4 = pitch >> 2;
             const float4 x0 = x[0];
             // float partial sums over blocks of 8 rows (shifted by the first sample), float64 across blocks
             double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
             for (; i + 8 <= n; i += 8) {
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = x[(i + u) * D4];
+                for (int u = 0; u < 8; ++u) v[u] = x[(i + u) * P4];
                 float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -86,7 +97,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
                 for (int c = 0; c < 4; ++c) { a[c] += (double)pa[c]; b[c] += (double)pb[c]; }
             }
             for (; i < n; ++i) {
-                const float4 v = x[i * D4];
+                const float4 v = x[i * P4];
                 const double e[4] = {(double)v.x - x0.x, (double)v.y - x0.y, (double)v.z - x0.z, (double)v.w - x0.w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { a[c] += e[c]; b[c] += e[c] * e[c]; }
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_moments_f32x4_kernel(const 
                 const double mean_s = a[c] / (double)n;
                 double var = (b[c] - (double)n * mean_s * mean_s) / (double)(n - 1);   // ddof = 1 (utils.py:111)
                 if (var < 0.0) var = 0.0;
-                const double mean = mean_s + xs[c];
+                const double mean = mean_s + (xs[c] - cshift[c]);
                 s_std[c] += sqrt(var); s_mean[c] += mean; s_mean2[c] += mean * mean;
             }
         }
@@ -120,8 +131,8 @@ constexpr int kShortThreads = 128;   // small blocks: several resident per SM, s
 // on the (warp-uniform) series length, so exactly n (n-1) / 2 difference terms are evaluated; per lag the terms are
 // added in increasing i, float partial sums as in the windowed kernel below.
 template <typename T, int NMAX, bool MOMENTS>
-__global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* __restrict__ q, long Nchain, long n, int D,
-                                                                  long stride_chain, int spb, int nlags,
+__global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* __restrict__ q, long Nchain, long n, int Dfull, long pitch,
+                                                                  long stride_chain, int d0, int D, int spb, int nlags,
                                                                   double* __restrict__ mom_out, double* __restrict__ out) {
     extern __shared__ double sm[];   // [NMAX + 3][D]
     for (int t = threadIdx.x; t < (NMAX + 3) * D; t += blockDim.x) sm[t] = 0.0;
@@ -135,13 +146,15 @@ __global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* _
 #pragma unroll
     for (int k = 0; k < NMAX - 1; ++k) acc[k] = T(0);
     double s_std = 0.0, s_mean = 0.0, s_mean2 = 0.0;
+    const double cshift = (double)q[d0 + d];     // see diag_moments_kernel
+    if (MOMENTS && blockIdx.x == 0 && sl == 0) mom_out[3 * Dfull + d0 + d] = cshift;
     if (sl < spb) {
         const long nseries = 2 * Nchain;
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
-            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0 + d;
             T v[NMAX];
 #pragma unroll
-            for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * D] : T(0);
+            for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * pitch] : T(0);
 #pragma unroll
             for (int i = 1; i < NMAX; ++i) {
                 if (i < n) {
@@ -159,7 +172,7 @@ __global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* _
                 const double mean_s = a / (double)n;
                 double var = (b - (double)n * mean_s * mean_s) / (double)(n - 1);
                 if (var < 0.0) var = 0.0;
-                const double mean = mean_s + x0;
+                const double mean = mean_s + (x0 - cshift);
                 s_std += sqrt(var); s_mean += mean; s_mean2 += mean * mean;
             }
         }
@@ -172,16 +185,16 @@ __global__ void __launch_bounds__(kShortThreads, 4) diag_short_kernel(const T* _
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
-    if (MOMENTS) for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(mom_out + t, sm[NMAX * D + t]);
+    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + (t / D) * Dfull + d0 + (t % D), sm[t]);
+    if (MOMENTS) for (int t = threadIdx.x; t < 3 * D; t += blockDim.x) atomicAdd(mom_out + (t / D) * Dfull + d0 + (t % D), sm[NMAX * D + t]);
 }
 
 // Lags t = lag0 + k, k < NL.  For every i the pair (x[i], x[i - lag0 - k]) contributes (x[i]-x[i-lag0-k])^2.
 // The last NL delayed values live in a register window addressed with compile-time indices (the time loop is
 // unrolled by NL); float partial sums are flushed into float64 every NL steps.
 template <typename T, int NL>
-__global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* __restrict__ q, long Nchain, long n, int D,
-                                                                      long stride_chain, int spb, int lag0, int nlags,
+__global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* __restrict__ q, long Nchain, long n, int Dfull, long pitch,
+                                                                      long stride_chain, int d0, int D, int spb, int lag0, int nlags,
                                                                       double* __restrict__ out) {
     extern __shared__ double sm[];   // [NL][D]
     for (int t = threadIdx.x; t < NL * D; t += blockDim.x) sm[t] = 0.0;
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
     if (sl < spb) {
         const long nseries = 2 * Nchain;
         for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
-            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * D + d;
+            const T* x = q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0 + d;
             T w[NL];         // w[(i - lag0) % NL] = x[i - lag0]
             T acc[NL];
 #pragma unroll
@@ -206,8 +219,8 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                 for (int r = 0; r < NL; ++r) {
                     const long i = i0 + r;
                     if (i < n) {
-                        const T xa = x[i * D];
-                        w[r] = x[(i - lag0) * D];
+                        const T xa = x[i * pitch];
+                        w[r] = x[(i - lag0) * pitch];
 #pragma unroll
                         for (int k = 0; k < NL; ++k) {
                             if (k <= r) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                 // is bound by load latency, not by HBM bandwidth: one resident block per SM at this register count)
                 T xa[NL], wn[NL];
 #pragma unroll
-                for (int r = 0; r < NL; ++r) { xa[r] = x[(i0 + r) * D]; wn[r] = x[(i0 + r - lag0) * D]; }
+                for (int r = 0; r < NL; ++r) { xa[r] = x[(i0 + r) * pitch]; wn[r] = x[(i0 + r - lag0) * pitch]; }
 #pragma unroll
                 for (int r = 0; r < NL; ++r) {
                     w[r] = wn[r];
@@ -238,8 +251,8 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
                 for (int r = 0; r < NL; ++r) {
                     const long i = i0 + r;
                     if (i < n) {
-                        const T xa = x[i * D];
-                        w[r] = x[(i - lag0) * D];
+                        const T xa = x[i * pitch];
+                        w[r] = x[(i - lag0) * pitch];
 #pragma unroll
                         for (int k = 0; k < NL; ++k) { const T df = xa - w[(r - k + NL) % NL]; acc[k] = fma(df, df, acc[k]); }
                     }
@@ -252,7 +265,176 @@ __global__ void __launch_bounds__(kDiagThreads) diag_variogram_kernel(const T* _
         for (int k = 0; k < NL; ++k) if (k < nlags) atomicAdd(&sm[k * D + d], dacc[k]);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + t, sm[t]);
+    for (int t = threadIdx.x; t < nlags * D; t += blockDim.x) atomicAdd(out + (t / D) * Dfull + d0 + (t % D), sm[t]);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed float32 kernels (D even): one thread owns TWO adjacent dimensions of one split chain, loads them as one 64-bit
+// word per sample and works on both with the packed FADD2 / FFMA2 instructions: one instruction per (sample, lag, dim).
+// ---------------------------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sqacc2(f32x2 d, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(d), "l"(c)); return r; }
+__device__ __forceinline__ float lo_of(f32x2 v) { return __uint_as_float((unsigned int)v); }
+__device__ __forceinline__ float hi_of(f32x2 v) { return __uint_as_float((unsigned int)(v >> 32)); }
+
+// Windowed variogram, lags t = lag0 + k, k < NL (utils.py:161-179).  Steps j = i - lag0 = 0, 1, ...: the pair
+// (x[lag0 + j], x[j - k]) contributes for k <= j.  The last NL delayed values live in a register window addressed with
+// compile-time indices (the step loop is unrolled by NL); both streams of half a block (NL / 2 steps) are requested up front.
+// Partial sums stay float32 within one split chain (n terms of like magnitude) and are widened once per chain.
+template <int NL>
+__global__ void __launch_bounds__(256, 2) diag_variogram_f32x2_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
+                                                                    long stride_chain, int d0, int Dt, int spb, int lag0, int nlags,
+                                                                    double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NL][Dt]
+    for (int t = threadIdx.x; t < NL * Dt; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int D2 = Dt >> 1;
+    const int dp = threadIdx.x % D2, sl = threadIdx.x / D2;
+    constexpr int H = NL / 2;
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        const long p2 = pitch >> 1;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const f32x2* x = reinterpret_cast<const f32x2*>(q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0) + dp;
+            f32x2 w[NL], acc[NL];
+#pragma unroll
+            for (int k = 0; k < NL; ++k) { w[k] = 0ull; acc[k] = 0ull; }
+            const long nsteps = n - lag0;                // j = 0 .. nsteps - 1
+            long j0 = 0;
+            if (nsteps > 0) {                            // first block: entry k valid only for k <= r (compile time)
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    f32x2 xa[H], wn[H];
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const long j = hb * H + r;
+                        xa[r] = (j < nsteps) ? x[(lag0 + j) * p2] : 0ull;
+                        wn[r] = (j < nsteps) ? x[j * p2] : 0ull;
+                    }
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const int rr = hb * H + r;
+                        if (rr < nsteps) {
+                            w[rr] = wn[r];
+#pragma unroll
+                            for (int k = 0; k < NL; ++k)
+                                if (k <= rr) acc[k] = sqacc2(sub2(xa[r], w[(rr - k + NL) % NL]), acc[k]);
+                        }
+                    }
+                }
+                j0 = NL;
+            }
+            for (; j0 + NL <= nsteps; j0 += NL) {        // steady state, no conditions
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    f32x2 xa[H], wn[H];
+#pragma unroll
+                    for (int r = 0; r < H; ++r) { xa[r] = x[(lag0 + j0 + hb * H + r) * p2]; wn[r] = x[(j0 + hb * H + r) * p2]; }
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const int rr = hb * H + r;
+                        w[rr] = wn[r];
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) acc[k] = sqacc2(sub2(xa[r], w[(rr - k + NL) % NL]), acc[k]);
+                    }
+                }
+            }
+            if (j0 < nsteps) {                           // tail
+#pragma unroll
+                for (int rr = 0; rr < NL; ++rr) {
+                    const long j = j0 + rr;
+                    if (j < nsteps) {
+                        const f32x2 xa = x[(lag0 + j) * p2];
+                        w[rr] = x[j * p2];
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) acc[k] = sqacc2(sub2(xa, w[(rr - k + NL) % NL]), acc[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                if (k < nlags) {
+                    atomicAdd(&sm[k * Dt + 2 * dp], (double)lo_of(acc[k]));
+                    atomicAdd(&sm[k * Dt + 2 * dp + 1], (double)hi_of(acc[k]));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
+}
+
+// Short series (n <= NMAX), packed: the n samples of two adjacent dimensions are loaded once, back to back, and the
+// moments and all lag sums are formed from registers (one HBM pass for the whole of utils.convergence_stats).
+template <int NMAX>
+__global__ void __launch_bounds__(128, 3) diag_short_f32x2_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
+                                                                 long stride_chain, int d0, int Dt, int spb, int nlags,
+                                                                 double* __restrict__ mom_out, double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NMAX + 3][Dt]
+    for (int t = threadIdx.x; t < (NMAX + 3) * Dt; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int D2 = Dt >> 1;
+    const int dp = threadIdx.x % D2, sl = threadIdx.x / D2;
+    f32x2 acc[NMAX - 1];
+#pragma unroll
+    for (int k = 0; k < NMAX - 1; ++k) acc[k] = 0ull;
+    double s_std[2] = {0.0, 0.0}, s_mean[2] = {0.0, 0.0}, s_mean2[2] = {0.0, 0.0};
+    double cshift[2] = {0.0, 0.0};               // see diag_moments_kernel
+    if (sl < spb) {
+        cshift[0] = (double)q[d0 + 2 * dp]; cshift[1] = (double)q[d0 + 2 * dp + 1];
+        if (mom_out && blockIdx.x == 0 && sl == 0) { mom_out[3 * D + d0 + 2 * dp] = cshift[0]; mom_out[3 * D + d0 + 2 * dp + 1] = cshift[1]; }
+        const long nseries = 2 * Nchain;
+        const long p2 = pitch >> 1;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const f32x2* x = reinterpret_cast<const f32x2*>(q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0) + dp;
+            f32x2 v[NMAX];
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * p2] : 0ull;
+#pragma unroll
+            for (int i = 1; i < NMAX; ++i) {
+                if (i < n) {
+#pragma unroll
+                    for (int k = 0; k < i; ++k) acc[k] = sqacc2(sub2(v[i], v[i - k - 1]), acc[k]);
+                }
+            }
+            if (mom_out) {           // per split chain mean and ddof = 1 standard deviation (utils.py:107-118)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float x0 = c ? hi_of(v[0]) : lo_of(v[0]);
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int i = 1; i < NMAX; ++i) {
+                        if (i < n) { const float e = (c ? hi_of(v[i]) : lo_of(v[i])) - x0; a += e; b = fmaf(e, e, b); }
+                    }
+                    const double mean_s = (double)a / (double)n;
+                    double var = ((double)b - (double)n * mean_s * mean_s) / (double)(n - 1);
+                    if (var < 0.0) var = 0.0;
+                    const double mean = mean_s + ((double)x0 - cshift[c]);
+                    s_std[c] += sqrt(var); s_mean[c] += mean; s_mean2[c] += mean * mean;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NMAX - 1; ++k) {
+            if (k < nlags) {
+                atomicAdd(&sm[k * Dt + 2 * dp], (double)lo_of(acc[k]));
+                atomicAdd(&sm[k * Dt + 2 * dp + 1], (double)hi_of(acc[k]));
+            }
+        }
+        if (mom_out) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                atomicAdd(&sm[(NMAX + 0) * Dt + 2 * dp + c], s_std[c]);
+                atomicAdd(&sm[(NMAX + 1) * Dt + 2 * dp + c], s_mean[c]);
+                atomicAdd(&sm[(NMAX + 2) * Dt + 2 * dp + c], s_mean2[c]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
+    if (mom_out) for (int t = threadIdx.x; t < 3 * Dt; t += blockDim.x) atomicAdd(mom_out + (t / Dt) * D + d0 + (t % Dt), sm[NMAX * Dt + t]);
 }
 
 int grid_for(long nseries, int spb, int per_sm = 8) {
@@ -274,87 +456,144 @@ int grid_for(long nseries, int spb, int per_sm = 8) {
         }                                 \
     } while (0)
 
+// Dimensions are processed in tiles of at most kDiagThreads (the thread <-> (series, dimension) mapping of the generic
+// kernels); D is limited only by the 32-bit tile arithmetic.
+static const int kMaxD = 1 << 20;
+
+static bool packed_ok(int32_t dtype, const void* q, int32_t D, int64_t pitch, int64_t stride_chain, int64_t n) {
+    return dtype == HMC_F32 && (D % 2) == 0 && (pitch % 2) == 0 && (stride_chain % 2) == 0 && ((n * pitch) % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(q) % 8) == 0 && getenv("HMC_B200_DIAG_GENERIC") == nullptr;
+}
+
 extern "C" int hmc_diag_moments(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
-                                double* out3xD, void* cuda_stream) {
-    HMC_REQUIRE(q && out3xD, "NULL buffer");
-    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kDiagThreads, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kDiagThreads);
+                                double* out4xD, void* cuda_stream) {
+    HMC_REQUIRE(dtype == HMC_F32 || dtype == HMC_F64, "dtype must be HMC_F32 or HMC_F64");
+    HMC_REQUIRE(q && out4xD, "NULL buffer");
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kMaxD, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kMaxD);
     HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const int spb = kDiagThreads / D;
-    const int grid = grid_for(2 * Nchain, spb);
-    const size_t smem = sizeof(double) * 3 * D;
-    HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, smem, stream));
-    const bool vec4 = dtype == HMC_F32 && (D % 4) == 0 && (stride_chain % 4) == 0 && (n * D) % 4 == 0 &&
+    const long pitch = D;
+    HMC_CUDA_CHECK(cudaMemsetAsync(out4xD, 0, sizeof(double) * 4 * D, stream));
+    const bool vec4 = dtype == HMC_F32 && (D % 4) == 0 && D <= 4 * kDiagThreads && (stride_chain % 4) == 0 && (n * D) % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(q) % 16) == 0;
     if (vec4) {
         const int spb4 = kDiagThreads / (D / 4);
-        diag_moments_f32x4_kernel<<<grid_for(2 * Nchain, spb4), kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb4, out3xD);
-    } else if (dtype == HMC_F32)
-        diag_moments_kernel<float><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, out3xD);
-    else
-        diag_moments_kernel<double><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, out3xD);
+        diag_moments_f32x4_kernel<<<grid_for(2 * Nchain, spb4), kDiagThreads, sizeof(double) * 3 * D, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, spb4, out4xD);
+    } else {
+        for (int d0 = 0; d0 < D; d0 += kDiagThreads) {
+            const int Dt = (D - d0 < kDiagThreads) ? D - d0 : kDiagThreads;
+            const int spb = kDiagThreads / Dt;
+            const int grid = grid_for(2 * Nchain, spb);
+            const size_t smem = sizeof(double) * 3 * Dt;
+            if (dtype == HMC_F32)
+                diag_moments_kernel<float><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, out4xD);
+            else
+                diag_moments_kernel<double><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, out4xD);
+        }
+    }
     HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
+template <typename T, bool MOMENTS>
+static int launch_short_generic(const T* q, int64_t Nchain, int64_t n, int32_t D, long pitch, int64_t stride_chain, int nlags,
+                                double* mom, double* out, cudaStream_t stream) {
+    constexpr int NL = 32;
+    for (int d0 = 0; d0 < D; d0 += kShortThreads) {
+        const int Dt = (D - d0 < kShortThreads) ? D - d0 : kShortThreads;
+        const int spb = kShortThreads / Dt;
+        const size_t smem = sizeof(double) * (NL + 3) * Dt;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<T, NL, MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_short_kernel<T, NL, MOMENTS><<<grid_for(2 * Nchain, spb, 8), kShortThreads, smem, stream>>>(q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, nlags, mom, out);
+    }
+    return HMC_OK;
+}
+
+static int launch_short_packed(const float* q, int64_t Nchain, int64_t n, int32_t D, long pitch, int64_t stride_chain, int nlags,
+                               double* mom, double* out, cudaStream_t stream) {
+    constexpr int NL = 32;
+    for (int d0 = 0; d0 < D; d0 += 2 * 128) {
+        const int Dt = (D - d0 < 256) ? D - d0 : 256;
+        const int spb = 128 / (Dt / 2);
+        const size_t smem = sizeof(double) * (NL + 3) * Dt;
+        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_f32x2_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        diag_short_f32x2_kernel<NL><<<grid_for(2 * Nchain, spb, 6), 128, smem, stream>>>(q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, nlags, mom, out);
+    }
     return HMC_OK;
 }
 
 extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
                                   int32_t lag0, int32_t nlags, double* out, void* cuda_stream) {
     constexpr int NL = 32;
+    HMC_REQUIRE(dtype == HMC_F32 || dtype == HMC_F64, "dtype must be HMC_F32 or HMC_F64");
     HMC_REQUIRE(q && out, "NULL buffer");
-    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kDiagThreads, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kDiagThreads);
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && D >= 1 && D <= kMaxD, "need Nchain >= 1, n >= 2, 1 <= D <= %d", kMaxD);
     HMC_REQUIRE(lag0 >= 1 && nlags >= 1 && nlags <= NL, "need lag0 >= 1 and 1 <= nlags <= %d", NL);
     HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const int spb = kDiagThreads / D;
-    const int grid = grid_for(2 * Nchain, spb);
-    const size_t smem = sizeof(double) * NL * D;
+    const long pitch = D;
     HMC_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * nlags * D, stream));
-    if (lag0 == 1 && n <= NL && D <= kShortThreads) {    // short series: one pass, values held in registers
-        const size_t smem2 = sizeof(double) * (NL + 3) * D;
-        if (dtype == HMC_F32) {
-            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<float, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            diag_short_kernel<float, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 8), kShortThreads, smem2, stream>>>((const float*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
-        } else {
-            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<double, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            diag_short_kernel<double, NL, false><<<grid_for(2 * Nchain, kShortThreads / D, 8), kShortThreads, smem2, stream>>>((const double*)q, Nchain, n, D, stride_chain, kShortThreads / D, nlags, nullptr, out);
+    const bool packed = packed_ok(dtype, q, D, pitch, stride_chain, n);
+    if (lag0 == 1 && n <= NL) {                  // short series: one pass, values held in registers
+        int rc;
+        if (packed) rc = launch_short_packed((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
+        else if (dtype == HMC_F32) rc = launch_short_generic<float, false>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
+        else rc = launch_short_generic<double, false>((const double*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
+        if (rc) return rc;
+        HMC_CUDA_CHECK(cudaGetLastError());
+        return HMC_OK;
+    }
+    if (packed) {
+        // 16 lags per pass, two resident blocks per SM (the 32-lag window needs 190+ registers and leaves one block per SM
+        // waiting on its loads); a 32-lag request is two passes, the second one reads the samples from L2 / HBM again
+        constexpr int NLP = 16;
+        for (int l0 = 0; l0 < nlags; l0 += NLP) {
+            const int nl = (nlags - l0 < NLP) ? nlags - l0 : NLP;
+            for (int d0 = 0; d0 < D; d0 += 512) {
+                const int Dt = (D - d0 < 512) ? D - d0 : 512;
+                const int spb = 256 / (Dt / 2);
+                const size_t smem = sizeof(double) * NLP * Dt;
+                HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_f32x2_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                diag_variogram_f32x2_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
+            }
         }
         HMC_CUDA_CHECK(cudaGetLastError());
         return HMC_OK;
     }
-    if (dtype == HMC_F32) {
-        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        diag_variogram_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);
-    } else {
-        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        diag_variogram_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, lag0, nlags, out);
+    for (int d0 = 0; d0 < D; d0 += kDiagThreads) {
+        const int Dt = (D - d0 < kDiagThreads) ? D - d0 : kDiagThreads;
+        const int spb = kDiagThreads / Dt;
+        const int grid = grid_for(2 * Nchain, spb);
+        const size_t smem = sizeof(double) * NL * Dt;
+        if (dtype == HMC_F32) {
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<float, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            diag_variogram_kernel<float, NL><<<grid, kDiagThreads, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0, nlags, out);
+        } else {
+            HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_kernel<double, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            diag_variogram_kernel<double, NL><<<grid, kDiagThreads, smem, stream>>>((const double*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0, nlags, out);
+        }
     }
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }
 
 extern "C" int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
-                                     int32_t nlags, double* out3xD, double* out_lags, void* cuda_stream) {
+                                     int32_t nlags, double* out4xD, double* out_lags, void* cuda_stream) {
     constexpr int NL = 32;
-    HMC_REQUIRE(q && out3xD && out_lags, "NULL buffer");
-    HMC_REQUIRE(Nchain >= 1 && n >= 2 && n <= NL && D >= 1 && D <= kShortThreads, "need Nchain >= 1, 2 <= n <= %d, 1 <= D <= %d", NL, kShortThreads);
+    HMC_REQUIRE(dtype == HMC_F32 || dtype == HMC_F64, "dtype must be HMC_F32 or HMC_F64");
+    HMC_REQUIRE(q && out4xD && out_lags, "NULL buffer");
+    HMC_REQUIRE(Nchain >= 1 && n >= 2 && n <= NL && D >= 1 && D <= kMaxD, "need Nchain >= 1, 2 <= n <= %d, 1 <= D <= %d", NL, kMaxD);
     HMC_REQUIRE(nlags >= 1 && nlags < NL, "need 1 <= nlags <= %d", NL - 1);
     HMC_REQUIRE(stride_chain >= 2 * n * D, "stride_chain too small");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    const int spb = kShortThreads / D;
-    const int grid = grid_for(2 * Nchain, spb, 8);            // 4 resident blocks per SM: two full waves
-    const size_t smem = sizeof(double) * (NL + 3) * D;
-    HMC_CUDA_CHECK(cudaMemsetAsync(out3xD, 0, sizeof(double) * 3 * D, stream));
+    const long pitch = D;
+    HMC_CUDA_CHECK(cudaMemsetAsync(out4xD, 0, sizeof(double) * 4 * D, stream));
     HMC_CUDA_CHECK(cudaMemsetAsync(out_lags, 0, sizeof(double) * nlags * D, stream));
-    if (dtype == HMC_F32) {
-        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<float, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        diag_short_kernel<float, NL, true><<<grid, kShortThreads, smem, stream>>>((const float*)q, Nchain, n, D, stride_chain, spb, nlags, out3xD, out_lags);
-    } else if (dtype == HMC_F64) {
-        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_kernel<double, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        diag_short_kernel<double, NL, true><<<grid, kShortThreads, smem, stream>>>((const double*)q, Nchain, n, D, stride_chain, spb, nlags, out3xD, out_lags);
-    } else {
-        hmc_set_error("dtype must be HMC_F32 or HMC_F64");
-        return HMC_E_BADARG;
-    }
+    int rc;
+    if (packed_ok(dtype, q, D, pitch, stride_chain, n)) rc = launch_short_packed((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
+    else if (dtype == HMC_F32) rc = launch_short_generic<float, true>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
+    else rc = launch_short_generic<double, true>((const double*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
+    if (rc) return rc;
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
 }

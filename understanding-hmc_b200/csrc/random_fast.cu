@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
         z.K0 = 0.f; z.Knew = 0.f; z.Einit = 0.0; z.Eprev = 0.0; z.V = 0.0; z.lnu = 0.f; z.pad = 0;
         bk[lane] = z;
     }
-    unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
+    unsigned long long n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
     GenArgs ga;
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
     ga.D = D; ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
             if (lane == s) {
                 SlotBk b = bk[s];
                 b.m = (int)m; b.it = itn; b.L = Ln; b.lnu = lnun; b.Knew = 0.5f * ksum; b.state = ST_RUN;
-                n_sumL += (unsigned int)Ln; n_sumL2 += (unsigned int)(Ln * Ln);
+                n_sumL += (unsigned long long)Ln; n_sumL2 += (unsigned long long)(Ln * Ln);
                 if (go) {
                     // E_initial of the new iteration (samplers.py:434-438): V at the accepted point + new kinetic energy
                     b.Einit = b.V + (double)b.Knew;
@@ -567,11 +567,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                 if ((tick & 1) == role) { do_gradient(); have_grad = true; }
                 else if (have_grad) { do_update(); do_service(); have_grad = false; running = any_running(); }
             }
-            if (lane == 0) done[warp] = running ? 0 : 1;
+            // flags double-buffered by tick parity: the partner may already be writing the flag of tick + 1 while this warp
+            // still reads the flags of this tick; both warps of a pair decide on the same snapshot
+            volatile int* dn = done + (tick & 1) * WARPS;
+            if (lane == 0) dn[warp] = (running || have_grad) ? 0 : 1;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
             PH_T(tT2);
             PH_ADD(4, tT0, tT2);
-            if (done[warp] && done[warp ^ 4] && !have_grad) break;
+            if (dn[warp] && dn[warp ^ 4]) break;
         }
     } else {
         while (running) {

@@ -102,16 +102,37 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// x = b1 + b2 + b3 exactly (three bf16 parts); the parts of two values packed as bf16x2 (lo = x0, hi = x1)
-__device__ __forceinline__ void split3(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1);
-    h1 = *reinterpret_cast<uint32_t*>(&a);
-    float r0 = x0 - __uint_as_float(h1 << 16), r1 = x1 - __uint_as_float(h1 & 0xffff0000u);
-    __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
-    h2 = *reinterpret_cast<uint32_t*>(&b);
-    r0 -= __uint_as_float(h2 << 16); r1 -= __uint_as_float(h2 & 0xffff0000u);
-    __nv_bfloat162 c = __floats2bfloat162_rn(r0, r1);
-    h3 = *reinterpret_cast<uint32_t*>(&c);
+// Split precisions of the gradient product (both FP32-grade, tests/test_bf16x3_split_cpu.py):
+//   PREC_BF16X3 : x = b1 + b2 + b3 exactly (three bf16 parts), six part products  (1,3)(3,1)(2,2)(1,2)(2,1)(1,1)
+//   PREC_FP16X2 : x = h1 + h2 + O(2^-23 x) (two fp16 parts), three part products  (1,2)(2,1)(1,1): the dropped terms are
+//                 at the level of the float32 rounding of x itself; needs |x| < 6e4 (the host checks the start points).
+// The residuals are formed with the mixed-precision subtract (one FHADD per value, half selector on the packed pair):
+//   r = h1 - x = -(x - h1),  h2' = rn(r) = -h2,  s = h2' - r = x - h1 - h2,  h3 = rn(s)
+// so the SECOND part comes out negated; the MMAs that read it set the negate-A bit of the instruction descriptor.
+enum : int { PREC_BF16X3 = 0, PREC_FP16X2 = 1 };
+template <int PREC> struct TcPrec;
+template <> struct TcPrec<PREC_BF16X3> { static constexpr int NPART = 3, NPROD = 6; };
+template <> struct TcPrec<PREC_FP16X2> { static constexpr int NPART = 2, NPROD = 3; };
+
+template <int PREC>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
+    float r0, r1;
+    if constexpr (PREC == PREC_BF16X3) {
+        float s0, s1;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(x1), "f"(x0));
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.bf16 %0, lo, %3;\n\tsub.rn.f32.bf16 %1, hi, %4;\n\t}"
+            : "=f"(r0), "=f"(r1) : "r"(h1), "f"(x0), "f"(x1));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(r1), "f"(r0));
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.bf16 %0, lo, %3;\n\tsub.rn.f32.bf16 %1, hi, %4;\n\t}"
+            : "=f"(s0), "=f"(s1) : "r"(h2), "f"(r0), "f"(r1));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h3) : "f"(s1), "f"(s0));
+    } else {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(x1), "f"(x0));
+        asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.f16 %0, lo, %3;\n\tsub.rn.f32.f16 %1, hi, %4;\n\t}"
+            : "=f"(r0), "=f"(r1) : "r"(h1), "f"(x0), "f"(x1));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(r1), "f"(r0));
+        h3 = 0u;
+    }
 }
 
 // tensor-memory stores of one warp: lane i writes TMEM lane (32 * (warp % 4) + i), consecutive 32-bit columns
@@ -139,40 +160,52 @@ __device__ __forceinline__ void lds4_if(int pr, uint32_t addr, float& a, float& 
                  : "+f"(a), "+f"(b), "+f"(c), "+f"(d) : "r"(addr), "r"(pr) : "memory");
 }
 
-// positions x[0..16) of a slice -> the three bf16 parts, TMEM columns acol .. acol+7 of each part
+// positions x[0..16) of a slice -> the parts, TMEM columns acol .. acol+7 of each part
+template <int PREC>
 __device__ __forceinline__ void put_half0(uint32_t acol, const float* x) {
     uint32_t w1[8], w2[8], w3[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) split3(x[2 * e], x[2 * e + 1], w1[e], w2[e], w3[e]);
-    tmem_st8(acol, w1); tmem_st8(acol + TC_APITCH, w2); tmem_st8(acol + 2 * TC_APITCH, w3);
+    for (int e = 0; e < 8; ++e) split_pair<PREC>(x[2 * e], x[2 * e + 1], w1[e], w2[e], w3[e]);
+    tmem_st8(acol, w1); tmem_st8(acol + TC_APITCH, w2);
+    if constexpr (TcPrec<PREC>::NPART == 3) tmem_st8(acol + 2 * TC_APITCH, w3);
 }
 // positions x[16..24) (x[16..28) for the wide slice) -> columns acol+8 .. acol+11 (.. acol+13)
+template <int PREC>
 __device__ __forceinline__ void put_half1(uint32_t acol, const float* x, bool wide) {
     uint32_t w1[6], w2[6], w3[6];
 #pragma unroll
-    for (int e = 0; e < 6; ++e) split3(x[16 + 2 * e], x[17 + 2 * e], w1[e], w2[e], w3[e]);
-    tmem_st4(acol + 8, w1); tmem_st4(acol + 8 + TC_APITCH, w2); tmem_st4(acol + 8 + 2 * TC_APITCH, w3);
-    if (wide) { tmem_st2(acol + 12, w1 + 4); tmem_st2(acol + 12 + TC_APITCH, w2 + 4); tmem_st2(acol + 12 + 2 * TC_APITCH, w3 + 4); }
+    for (int e = 0; e < 6; ++e) split_pair<PREC>(x[16 + 2 * e], x[17 + 2 * e], w1[e], w2[e], w3[e]);
+    tmem_st4(acol + 8, w1); tmem_st4(acol + 8 + TC_APITCH, w2);
+    if constexpr (TcPrec<PREC>::NPART == 3) tmem_st4(acol + 8 + 2 * TC_APITCH, w3);
+    if (wide) {
+        tmem_st2(acol + 12, w1 + 4); tmem_st2(acol + 12 + TC_APITCH, w2 + 4);
+        if constexpr (TcPrec<PREC>::NPART == 3) tmem_st2(acol + 12 + 2 * TC_APITCH, w3 + 4);
+    }
 }
 
-// The 42 MMAs of a gradient pass: six part products, small terms first: (1,3) (3,1) (2,2) (1,2) (2,1) (1,1), seven
-// K steps each.  A from tensor memory (part pa, 8 columns per K step), B descriptor = constant high word + start address
-// (>> 4) in the low word; the per-MMA offsets are immediates inside the asm so that nothing is hoisted into registers.
-template <int I>
+// The MMAs of a gradient pass: the part products, small terms first -- bf16x3: (1,3) (3,1) (2,2) (1,2) (2,1) (1,1), fp16x2:
+// (1,2) (2,1) (1,1) -- seven K steps each.  A from tensor memory (part pa, 8 columns per K step; part 2 is stored negated,
+// its products set the negate-A bit), B descriptor = constant high word + start address (>> 4) in the low word; the
+// per-MMA offsets are immediates inside the asm so that nothing is hoisted into registers.
+template <int PREC, int I>
 __device__ __forceinline__ void tc_mma_all(uint32_t tmem, uint32_t dlo, uint32_t dhi, uint32_t idesc) {
-    if constexpr (I < 6 * (TC_KP / 16)) {
-        constexpr int pa[6] = {0, 2, 1, 0, 1, 0}, pb[6] = {2, 0, 1, 1, 0, 0};
+    if constexpr (I < TcPrec<PREC>::NPROD * (TC_KP / 16)) {
+        constexpr int pa3[6] = {0, 2, 1, 0, 1, 0}, pb3[6] = {2, 0, 1, 1, 0, 0};
+        constexpr int pa2[3] = {0, 1, 0}, pb2[3] = {1, 0, 0};
         constexpr int t = I / (TC_KP / 16), ks = I % (TC_KP / 16);
+        constexpr int pa = (PREC == PREC_BF16X3) ? pa3[t % 6] : pa2[t % 3], pb = (PREC == PREC_BF16X3) ? pb3[t % 6] : pb2[t % 3];
         asm volatile(
-            "{\n\t.reg .pred pacc;\n\t.reg .b32 ta, bl;\n\t.reg .b64 db;\n\t"
+            "{\n\t.reg .pred pacc;\n\t.reg .b32 ta, bl, id;\n\t.reg .b64 db;\n\t"
             "setp.ne.b32 pacc, %4, 0;\n\t"
             "add.u32 ta, %0, %5;\n\t"
             "add.u32 bl, %1, %6;\n\t"
+            "or.b32 id, %3, %8;\n\t"
             "mov.b64 db, {bl, %2};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, {%7, %7, %7, %7}, pacc;\n\t}"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, id, {%7, %7, %7, %7}, pacc;\n\t}"
             ::"r"(tmem), "r"(dlo), "r"(dhi), "r"(idesc), "r"(I ? 1u : 0u),
-              "n"((int)(TC_ACOL + pa[t] * TC_APITCH + 8 * ks)), "n"((pb[t] * TC_BPART + ks * 2 * TC_KP * 16) >> 4), "r"(0u));
-        tc_mma_all<I + 1>(tmem, dlo, dhi, idesc);
+              "n"((int)(TC_ACOL + pa * TC_APITCH + 8 * ks)), "n"((pb * TC_BPART + ks * 2 * TC_KP * 16) >> 4), "r"(0u),
+              "n"(pa == 1 ? (1 << 13) : 0));
+        tc_mma_all<PREC, I + 1>(tmem, dlo, dhi, idesc);
     }
 }
 
@@ -246,12 +279,13 @@ struct TcShared {                       // small per-chain arrays in shared memo
 constexpr int OUT_SAMPLE = 1 << 29, OUT_STATE = 1 << 30;   // copy the chain's start-point row to q_chain[m][idx] / to state_q[m]
 constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
-template <bool UDT>
+template <bool UDT, int PREC>
 __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue, int* progress, int nsb, int SB) {
     constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* Bp = smem;                                   // 3 parts [KC][112] 16-byte chunks
-    float* mu_s = reinterpret_cast<float*>(Bp + 3 * TC_BPART);  // [KP]
+    constexpr int NPART = TcPrec<PREC>::NPART;
+    unsigned char* Bp = smem;                                   // NPART parts [KC][112] 16-byte chunks
+    float* mu_s = reinterpret_cast<float*>(Bp + NPART * TC_BPART);  // [KP]
     float* dt_s = mu_s + KP;                                    // [KP]
     float* stage_all = dt_s + KP;                               // [128][TC_SROW] momentum staging, one row per chain
     float* q0_s = stage_all + TC_M * TC_SROW;                   // [128][TC_SROW] shifted start position of the trajectory
@@ -281,11 +315,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 const int k0 = kc * 8 + 2 * e, k1 = k0 + 1;
                 const float x0 = (n < D && k0 < D) ? Ft[(size_t)k0 * Dpad + n] : 0.f;
                 const float x1 = (n < D && k1 < D) ? Ft[(size_t)k1 * Dpad + n] : 0.f;
-                split3(x0, x1, w1[e], w2[e], w3[e]);
+                split_pair<PREC>(x0, x1, w1[e], w2[e], w3[e]);
+                w2[e] ^= 0x80008000u;                           // split_pair returns the second part negated; B holds it as is
             }
             reinterpret_cast<uint4*>(Bp)[t] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
             reinterpret_cast<uint4*>(Bp + TC_BPART)[t] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-            reinterpret_cast<uint4*>(Bp + 2 * TC_BPART)[t] = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+            if constexpr (NPART == 3) reinterpret_cast<uint4*>(Bp + 2 * TC_BPART)[t] = make_uint4(w3[0], w3[1], w3[2], w3[3]);
         }
         for (int t = tid; t < KP; t += TC_NT) {
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
@@ -312,7 +347,9 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     TC_MARK(3);
     const uint32_t tmem_row = tmem + ((uint32_t)(grp * 32) << 16) + (uint32_t)j0;                   // my accumulator slice
     const uint32_t acol = tmem + ((uint32_t)(grp * 32) << 16) + TC_ACOL + 12u * (uint32_t)(slice & 3);  // my A-part columns
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // instruction descriptor: D = f32 (bits 4-5), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16), N >> 3 (17-22), M >> 4 (24-28)
+    constexpr uint32_t fmt = (PREC == PREC_BF16X3) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
     float* q_chain = (float*)a.q_chain;
@@ -356,7 +393,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint64_t dsc = make_desc(smem_u32(Bp), KP * 16, 128);
                     const uint32_t dlo = (uint32_t)dsc, dhi = (uint32_t)(dsc >> 32);
-                    tc_mma_all<0>(tmem, dlo, dhi, idesc);
+                    tc_mma_all<PREC, 0>(tmem, dlo, dhi, idesc);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
     #ifdef HMC_PROFILE_PHASES
                     tph4 += clock64() - ti0;
@@ -431,7 +468,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     int pn = 0;                      // pass number
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
-    unsigned int n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;
+    unsigned long long n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;   // 64-bit: sum L^2 of a long launch exceeds 2^32
     uint32_t phase = 0;
     bool have_grad = false;          // a gradient pass has been issued and its accumulator is to be consumed
 #ifdef HMC_PROFILE_PHASES
@@ -439,12 +476,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #endif
 
     {                                // defined operand rows before the first pass: all parts zero (K padding included)
-        put_half0(acol, x);
-        put_half1(acol, x, true);    // the wide form also clears columns 12, 13 of the slice; harmless for the others
+        put_half0<PREC>(acol, x);
+        put_half1<PREC>(acol, x, true);    // the wide form also clears columns 12, 13 of the slice; harmless for the others
         if (wide) {                  // K padding: dims 100..111 = columns 50..55 of each part
             const uint32_t z[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int pt = 0; pt < 3; ++pt) {
+            for (int pt = 0; pt < NPART; ++pt) {
                 tmem_st4(acol + 14 + pt * TC_APITCH, z);
                 tmem_st2(acol + 18 + pt * TC_APITCH, z);
             }
@@ -478,7 +515,12 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + 4 * c));
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
                             if (fresh) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
-                            *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(v.x - mu4.x, v.y - mu4.y, v.z - mu4.z, v.w - mu4.w);
+                            const float4 d4 = make_float4(v.x - mu4.x, v.y - mu4.y, v.z - mu4.z, v.w - mu4.w);
+                            *reinterpret_cast<float4*>(q0r + 4 * c) = d4;
+                            if constexpr (PREC == PREC_FP16X2) {       // start point outside the range of the fp16 split: tell the host
+                                if (fresh && !(fmaxf(fmaxf(fabsf(d4.x), fabsf(d4.y)), fmaxf(fabsf(d4.z), fabsf(d4.w))) < 16384.f))
+                                    atomicOr(progress + a.Nchain, 1);
+                            }
                         }
                     }
                 } else {                                              // no chain left for this slot: zero rows
@@ -549,7 +591,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 p[jj] = pn;
                 x[jj] = fmaf(pn, UDT ? ddt : dwt * dtj, x[jj]);
             }
-            put_half0(acol, x);
+            put_half0<PREC>(acol, x);
             tmem_ld16(tmem_row + 16u, gv);
 #pragma unroll
             for (int jj = 16; jj < 28; ++jj) {
@@ -563,7 +605,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     x[jj] = fmaf(pn, UDT ? ddt : dwt * dtj, x[jj]);
                 }
             }
-            put_half1(acol, x, wide);
+            put_half1<PREC>(acol, x, wide);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             sh->red[slice][chain] = make_float2(hv, hk);
             if (tr && (md == MODE_FIRST || md == MODE_MID)) {
@@ -575,8 +617,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             TP_T(t2);
             TP_ADD(1, t1, t2);
         } else {                                                // first pass: rows of the chains loaded by nobody yet
-            put_half0(acol, x);
-            put_half1(acol, x, wide);
+            put_half0<PREC>(acol, x);
+            put_half1<PREC>(acol, x, wide);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         TC_MARK(22);
@@ -603,7 +645,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     // the draws of this iteration (requested at least two passes ago): samplers.py:431, 441
                     const float Knew = 0.5f * sh->gK[chain];
                     L = sh->gL[chain]; lnu = sh->glnu[chain];
-                    n_sumL += (unsigned int)L; n_sumL2 += (unsigned int)(L * L);
+                    n_sumL += (unsigned long long)L; n_sumL2 += (unsigned long long)(L * L);
                     if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                     // samplers.py:444
                     if (init) {                                                 // samplers.py:416-420
                         const float E0 = V + 0.5f * sh->gK0[chain];
@@ -784,11 +826,11 @@ extern "C" int hmc_debug_tc_cycles(unsigned long long* out16, int reset) {
 }
 #endif
 
-constexpr size_t tc_smem_bytes() {
-    return 3 * (size_t)TC_BPART + sizeof(float) * (2 * TC_KP + 2 * TC_M * TC_SROW) + sizeof(TcShared) + 64;
+constexpr size_t tc_smem_bytes(int npart) {
+    return (size_t)npart * TC_BPART + sizeof(float) * (2 * TC_KP + 2 * TC_M * TC_SROW) + sizeof(TcShared) + 64;
 }
 
-static_assert(tc_smem_bytes() <= 232448, "shared memory of the tensor-core kernel exceeds 227 KB");
+static_assert(tc_smem_bytes(3) <= 232448, "shared memory of the tensor-core kernel exceeds 227 KB");
 
 bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
@@ -799,10 +841,21 @@ bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
     return true;
 }
 
+template <bool UDT, int PREC>
+static int tc_launch(const hmc_random_args& a, int grid, unsigned int* queue, int* progress, int nsb, int SB, cudaStream_t stream) {
+    const size_t smem = tc_smem_bytes(TcPrec<PREC>::NPART);
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(hmc_random_tc_kernel<UDT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hmc_random_tc_kernel<UDT, PREC><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
 int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
-    const size_t smem = tc_smem_bytes();
-    const bool udt = (a.flags & 1) != 0;                 // bit 0: the step size is the same for all dimensions
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(udt ? hmc_random_tc_kernel<true> : hmc_random_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool udt = (a.flags & HMC_FLAG_UNIFORM_DT) != 0;      // the step size is the same for all dimensions
+    // fp16x2 split (three part products instead of six) when the caller vouches for the range of q - mu (flags bit 1);
+    // HMC_B200_TC_PREC=bf16x3|fp16x2 overrides (tests, measurements)
+    bool fp16 = (a.flags & HMC_FLAG_TC_FP16X2) != 0;
+    if (const char* e = getenv("HMC_B200_TC_PREC")) fp16 = (e[0] == 'f');
     int dev = 0, sms = 0;
     HMC_CUDA_CHECK(cudaGetDevice(&dev));
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -820,9 +873,10 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     nsb = (niter + SB - 1) / SB;
     unsigned int* queue = (unsigned int*)a.state_g;             // [0] queue head, [16 .. 16 + Nchain) per-chain progress
     int* progress = (int*)a.state_g + 16;
-    HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * (16 + (size_t)a.Nchain), stream));
-    if (udt) hmc_random_tc_kernel<true><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
-    else hmc_random_tc_kernel<false><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
-    HMC_CUDA_CHECK(cudaGetLastError());
-    return HMC_OK;
+    // (one more word behind the progress counters: "a start point left the fp16 range", kept across the launches of a run)
+    HMC_CUDA_CHECK(cudaMemsetAsync(queue, 0, sizeof(int) * (16 + (size_t)a.Nchain + (a.iter_begin == 0 ? 1 : 0)), stream));
+    if (fp16) return udt ? tc_launch<true, PREC_FP16X2>(a, grid, queue, progress, nsb, SB, stream)
+                         : tc_launch<false, PREC_FP16X2>(a, grid, queue, progress, nsb, SB, stream);
+    return udt ? tc_launch<true, PREC_BF16X3>(a, grid, queue, progress, nsb, SB, stream)
+               : tc_launch<false, PREC_BF16X3>(a, grid, queue, progress, nsb, SB, stream);
 }

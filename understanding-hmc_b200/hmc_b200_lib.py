@@ -14,10 +14,12 @@ LIB_PATH = os.path.join(_HERE, "libhmc_b200.so")
 HMC_F32, HMC_F64 = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC = 0, 1, 2, 3
 KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST, "tc": KERNEL_TC}
+FLAG_UNIFORM_DT, FLAG_TC_FP16X2 = 1, 2
 HMC_OK, HMC_E_BADARG, HMC_E_UNSUPPORTED, HMC_E_CUDA, HMC_E_DMAX = 0, 1, 2, 3, 4
 
 EXPORTS = ["hmc_random_run", "hmc_nuts_run", "hmc_diag_moments", "hmc_diag_variogram", "hmc_diag_short_series", "hmc_philox_draws",
-           "hmc_ffma_peak", "hmc_version", "hmc_last_error_string"]
+           "hmc_ffma_peak", "hmc_version", "hmc_last_error_string", "hmc_start_pts", "hmc_summary_moments", "hmc_summary_hist",
+           "hmc_summary_select"]
 
 
 class Target(C.Structure):
@@ -77,6 +79,18 @@ def load():
     lib.hmc_philox_draws.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hmc_philox_draws.restype = C.c_int
+    lib.hmc_start_pts.argtypes = [C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    lib.hmc_start_pts.restype = C.c_int
+    lib.hmc_summary_moments.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_void_p]
+    lib.hmc_summary_moments.restype = C.c_int
+    lib.hmc_summary_hist.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hmc_summary_hist.restype = C.c_int
+    lib.hmc_summary_select.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_uint64,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hmc_summary_select.restype = C.c_int
     lib.hmc_ffma_peak.argtypes = [C.POINTER(C.c_double), C.c_int32, C.c_void_p]
     lib.hmc_ffma_peak.restype = C.c_int
     lib.hmc_version.argtypes = []

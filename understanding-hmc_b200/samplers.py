@@ -10,7 +10,9 @@ Extra keyword-only constructor arguments (defaults keep the reference behaviour)
   dtype="float32"|"float64", seed=0 (Philox key), kernel="auto"|"generic"|"fast"|"tc", draws=None (the reference's
   own draws as structured tapes, see tests/golden/make_golden.py), on_dmax="assert"|"stop" (NUTS),
   chain_id0=0 / distributed=False (chains sharded over ranks; counters and moments are all-reduced),
-  iter_block=None (iterations per kernel launch), target=None (explicit ``MVNSpec`` instead of probing V/dVdq).
+  iter_block=None (iterations per kernel launch), target=None (explicit ``MVNSpec`` instead of probing V/dVdq),
+  tc_precision="auto"|"fp16x2"|"bf16x3" (split of the tensor-core gradient product; "auto" = fp16x2, re-run with bf16x3
+  when a start point leaves the fp16 range or the target's scale is far below 1).
 """
 import os
 
@@ -123,10 +125,70 @@ class sampler(object):
         self.R_q, self.n_eff_q = _utils.convergence_stats(src[:, 1:, :], warm_up_num=0, thin_rate=1, group=group)
         return
 
+    def sample_summary(self, xmax=None, dx=None):
+        """Everything ``plot_samples`` derives from the samples (samplers.py:84-113, 160-186, 209-250), computed by GPU
+        reductions over the device-resident outputs (csrc/summary.cu): per-dimension mean / variance over stored samples
+        1.., 2.5 / 97.5 percentiles, plot ranges and histograms of q1, q2 (all stored samples) and of the centred energies
+        E and the energy differences dE (stored samples 1..).  Sharded runs all-reduce the counts."""
+        q = self._q_dev
+        assert q is not None, "sample_summary needs a finished gen_sample"
+        group = None if getattr(self, "distributed", False) else False
+        out = {}
+        out["q_mean"], out["q_var"] = _utils.device_moments(q[:, 1:, :], group=group)         # samplers.py:209-216, 244-250
+
+        def rng_of(x, N):
+            lo, hi = _utils.device_percentile(x, [2.5, 97.5], group=group)                     # samplers.py:97-103
+            c, r = (hi + lo) / 2., (hi - lo) * 2.5
+            return c - r / 2., c + r / 2., r
+
+        for name, col in (("q1", 0), ("q2", 1)):
+            if col >= self.D:
+                continue
+            x = q[:, :, col]
+            if xmax is None:
+                lo, hi, r = rng_of(x, None)
+            else:
+                lo, hi, r = -xmax, xmax, 2. * xmax                                             # samplers.py:117-121
+            w = r / 100. if dx is None else dx                                                 # samplers.py:124-128
+            edges = np.arange(lo, hi, w)
+            out[name + "_range"] = (lo, hi)
+            out[name + "_edges"] = edges
+            out[name + "_hist"] = _utils.device_histogram(x, edges, group=group)[0]             # samplers.py:160-175
+        E, dE = getattr(self, "_E_dev", None), getattr(self, "_dE_dev", None)
+        if E is not None and E.shape[1] > 1:
+            Em, _ = _utils.device_moments(E[:, 1:, None], group=group)                         # samplers.py:86-87
+            out["E_mean"] = float(Em[0])
+            lo, hi = _utils.device_percentile(E[:, 1:], [2.5, 97.5], group=group) - out["E_mean"]   # samplers.py:177-183
+            c, r = (lo + hi) / 2., (hi - lo) * 2.5
+            edges = np.arange(c - r / 2., c + r / 2., r / 100.)
+            out["E_range"] = (c - r / 2., c + r / 2.)
+            out["E_edges"] = edges
+            out["E_hist"] = _utils.device_histogram(E[:, 1:], edges, shift=out["E_mean"], group=group)[0]
+            out["dE_hist"] = _utils.device_histogram(dE[:, 1:], edges, group=group)[0]         # samplers.py:184-186
+        return out
+
     def plot_samples(self, title_prefix, show=False, savefig=False, xmax=None, dx=None, plot_normal=True,
                      plot_cov=True, q0=None, cov0=None):
-        """3x3 summary figure (samplers.py:67-291): presentation, out of scope of the B200 hot path."""
-        print("plot_samples: plotting is outside the B200 hot-path build (SURVEY section 2); skipped for %s" % title_prefix)
+        """3x3 summary figure (samplers.py:67-291).  Drawing is presentation and outside the B200 hot-path build; the
+        numbers the figure shows are computed on the GPU (``sample_summary``) and printed instead."""
+        if self._q_dev is None:
+            print("plot_samples: no device samples; skipped for %s" % title_prefix)
+            return
+        s = self.sample_summary(xmax=xmax, dx=dx)
+        self.summary = s
+        print("plot_samples[%s]: D/Nchain/Niter/Warm-up/Thin = %d/%d/%d/%d/%d (figure not drawn: plotting is outside the hot path)"
+              % (title_prefix, self.D, self.Nchain, self.Niter, self.warm_up_num, self.thin_rate))
+        if q0 is not None:
+            print("  bias(mean) min/max: %.3e / %.3e" % (np.min(s["q_mean"] - q0), np.max(s["q_mean"] - q0)))
+        if cov0 is not None:
+            ratio = s["q_var"] / np.diag(np.asarray(cov0))
+            print("  estimated/true variance min/max: %.4f / %.4f" % (ratio.min(), ratio.max()))
+        if self.R_q is not None:
+            print("  R med/std: %.3f / %.3f" % (np.median(self.R_q), np.std(self.R_q)))
+            print("  Ntot/eff med: %.1E/%.1E" % (self.L_chain * self.Nchain, np.median(self.n_eff_q)))
+            print("  #steps/ES med: %.2E" % (self.N_total_steps / np.median(self.n_eff_q)))
+        if self.accept_R is not None:
+            print("  RA after warm-up: %.3f" % self.accept_R)
         return
 
 
@@ -137,7 +199,7 @@ class HMC_sampler(sampler):
                  cov_p=None, sampler_type="Fixed", L=None, global_dt=True, dt=None,
                  L_low=None, L_high=None, log2L=None, d_max=10, *,
                  dtype="float32", seed=0, kernel="auto", draws=None, on_dmax="assert", chain_id0=0,
-                 distributed=False, iter_block=None, target=None):
+                 distributed=False, iter_block=None, target=None, tc_precision="auto"):
         sampler.__init__(self, D=D, target_lnL=None, Nchain=Nchain, Niter=Niter, thin_rate=thin_rate,
                          warm_up_num=warm_up_num)
         self.V = V
@@ -176,6 +238,8 @@ class HMC_sampler(sampler):
         assert dtype in ("float32", "float64")
         assert kernel in _L.KERNELS
         assert on_dmax in ("assert", "stop")
+        assert tc_precision in ("auto", "fp16x2", "bf16x3")
+        self.tc_precision = tc_precision
         self.dtype = dtype
         self.seed = int(seed)
         self.kernel = kernel
@@ -288,15 +352,16 @@ class HMC_sampler(sampler):
         f64 = torch.float64
         owns0 = self.chain_id0 == 0
         save_chain = N_save_chain0 > 0
-        self._q_dev = torch.empty((Nc, Lc, D), dtype=tdt, device=dev)     # every stored sample is written by the kernel
-        self._E_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
-        self._dE_dev = torch.zeros((Nc, Lc), dtype=f64, device=dev)
+        self._q_dev = torch.empty((Nc, Lc, D), dtype=tdt, device=dev)     # every stored sample / energy is written by the kernel
+        self._E_dev = torch.empty((Nc, Lc), dtype=f64, device=dev)
+        self._dE_dev = torch.empty((Nc, Lc), dtype=f64, device=dev)
         self._q_host = self._E_host = self._dE_host = None
         keep["qs"] = self._to_device(torch, q_start, dev, tdt)
         keep["state_q"] = torch.empty((Nc, D), dtype=tdt, device=dev)
-        keep["state_g"] = torch.zeros((max(Nc * D, 64),), dtype=tdt, device=dev)
-        keep["state_e"] = torch.zeros((Nc,), dtype=f64, device=dev)
-        counters = torch.zeros((4,), dtype=torch.int64, device=dev)
+        # scratch: work-queue head, per-chain progress words, range flag (cleared by the launches themselves)
+        keep["state_g"] = torch.empty((Nc + 64,), dtype=torch.float64, device=dev)
+        keep["state_e"] = torch.empty((Nc,), dtype=f64, device=dev)
+        counters = torch.zeros((8,), dtype=torch.int64, device=dev)      # [0..4) kernel counters, [4] chains of this rank
         a = _L.RandomArgs()
         a.dtype = _L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64
         a.kernel = _L.KERNELS[self.kernel]
@@ -306,7 +371,12 @@ class HMC_sampler(sampler):
         a.N_save_chain0 = int(N_save_chain0) if owns0 else 0
         a.seed = self.seed
         a.target = tgt
-        a.flags = 1 if np.ndim(self.dt) == 0 or np.all(np.asarray(self.dt) == np.asarray(self.dt).flat[0]) else 0
+        a.flags = _L.FLAG_UNIFORM_DT if np.ndim(self.dt) == 0 or np.all(np.asarray(self.dt) == np.asarray(self.dt).flat[0]) else 0
+        # two-part fp16 split of the tensor-core gradient product unless the target's scale is far below 1 (fp16 subnormals);
+        # start points outside the fp16 range are reported by the kernel (state_g word 16 + Nchain) and the run is repeated with bf16x3
+        small = float(np.min(1.0 / np.sqrt(np.abs(np.diag(self.target.P))))) < 2.0 ** -10
+        if self.tc_precision == "fp16x2" or (self.tc_precision == "auto" and not small):
+            a.flags |= _L.FLAG_TC_FP16X2
         a.flags |= (int(os.environ.get("HMC_B200_TILE_VARIANT", "0")) & 0xff) << 8      # tuning knob
         a.q_start = keep["qs"].data_ptr()
         if self.draws is not None:
@@ -349,13 +419,22 @@ class HMC_sampler(sampler):
         ev1.record()
         ev1.synchronize()
         self.kernel_ms = ev0.elapsed_time(ev1)
+        if (a.flags & _L.FLAG_TC_FP16X2) and self.tc_precision == "auto" and Nc * D >= 64 and \
+                int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0 and self.kernel in ("auto", "tc"):
+            # a start point left the range of the fp16 split (tensor-core kernel only): repeat with the bf16x3 split
+            self.tc_precision = "bf16x3"
+            return self.gen_sample_random(q_start, N_save_chain0, verbose, quiet)
         if verbose:                                                                  # samplers.py:478-481 (Q10)
             self.dt_total += self.kernel_ms * 1e-3
             say("Time taken: %.2f\n" % (self.kernel_ms * 1e-3))
-        self.sum_L_local = int(counters[2].item())
-        c = self._all_reduce(torch, counters.clone()).cpu().numpy()
-        nchain_all = self._all_reduce(torch, torch.tensor([Nc], dtype=torch.int64, device=dev)).item()
-        acc_warm, acc_post, sumL, sumL2 = (int(v) for v in c)
+        # one packed buffer: local counters and chain count, all-reduced copy behind them -> one collective, one D2H
+        counters[4] = Nc
+        if self.distributed:
+            both = torch.cat([counters, self._all_reduce(torch, counters.clone())]).cpu().numpy()
+        else:
+            both = torch.cat([counters, counters]).cpu().numpy()
+        self.sum_L_local = int(both[2])
+        acc_warm, acc_post, sumL, sumL2, nchain_all = (int(v) for v in both[8:13])
         self.sum_L = sumL
         self.N_total_steps = nchain_all * (1 + 2 * self.Niter) + D * sumL2          # samplers.py:417,435,450,456 (Q3)
         say("Compute acceptance rate")

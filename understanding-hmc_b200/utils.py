@@ -36,41 +36,15 @@ import hmc_b200_lib as _L  # noqa: E402
 
 
 # ----------------------------------------------------------------------------------------------------------
-# Plot helpers (utils.py:21-71): geometry is kept, drawing needs matplotlib.
+# Plot helpers (utils.py:21-71) are presentation code outside the hot path: the names stay
+# importable for `from utils import *`, the drawing itself is not part of this build.
 # ----------------------------------------------------------------------------------------------------------
 def cov_ellipse(cov, q=None, nsig=None, **kwargs):
-    """Width, height and rotation of a covariance ellipse (utils.py:21-53)."""
-    if q is not None:
-        q = np.asarray(q)
-    elif nsig is not None:
-        q = 2 * norm.cdf(nsig) - 1
-    else:
-        raise ValueError("One of `q` and `nsig` should be specified.")
-    r2 = chi2.ppf(q, 2)
-    val, vec = np.linalg.eigh(cov)
-    width, height = 2 * np.sqrt(val[:, None] * r2)
-    rotation = np.degrees(np.arctan2(*vec[::-1, 0]))
-    return width, height, rotation
+    raise NotImplementedError("cov_ellipse: plotting geometry is outside the B200 hot-path build (SURVEY section 2)")
 
 
 def plot_cov_ellipse(ax, mus, covs, var_num1, var_num2, MoG_color="Blue", lw=2):
-    """1- and 2-sigma ellipses (utils.py:55-71); a no-op notice without matplotlib."""
-    if not HAVE_MPL:
-        print("plot_cov_ellipse: matplotlib not available, skipped")
-        return
-    N_ellip = len(mus)
-    for i in range(N_ellip):
-        cov = np.asarray(covs[i])
-        cov = [[cov[var_num1, var_num1], cov[var_num1, var_num2]], [cov[var_num2, var_num1], cov[var_num2, var_num2]]]
-        mu = np.asarray(mus[i])
-        mu = [mu[var_num1], mu[var_num2]]
-        for j in [1, 2]:
-            width, height, theta = cov_ellipse(cov, q=None, nsig=j)
-            e = Ellipse(xy=mu, width=width, height=height, angle=theta, lw=lw)
-            ax.add_artist(e)
-            e.set_alpha(1)
-            e.set_facecolor("none")
-            e.set_edgecolor(MoG_color)
+    print("plot_cov_ellipse: plotting is outside the B200 hot-path build (SURVEY section 2); skipped")
     return
 
 
@@ -128,39 +102,63 @@ def _finish_n_eff(var, V_rows, m, n, state):
     return bool(np.all(st.done))
 
 
-def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32):
+ROW_SHIFT, ROW_COUNT, ROW_LAGS = 3, 4, 5        # layout of the packed statistics buffer [5 + lag_chunk][D]
+
+
+def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32, device=None):
     """Rhat / n_eff from per-rank partial sums (utils.py:107-157).
 
-    ``moments_fn()`` -> float64 tensor (3, D): sum_j std_j, sum_j mean_j, sum_j mean_j^2 over the LOCAL split
-    chains; ``variogram_fn(lag0, nl)`` -> float64 tensor (nl, D) of local variogram numerators.  When
-    torch.distributed is initialised (and ``group is not False``) the partials are all-reduced (sum) -- the only
-    collective on the whole path; everything after that is O(lags * D) host arithmetic."""
+    ``moments_fn(buf)`` fills the float64 buffer ``buf`` [5 + lag_chunk][D]: rows 0..2 = sum_j std_j, sum_j (mean_j - c),
+    sum_j (mean_j - c)^2 over the LOCAL split chains, row 3 = the rank's shift c (the first sample of its first chain, so
+    that nothing cancels when the chains sit far from zero); it may also fill rows 5.. with the variogram numerators of
+    lags 1..lag_chunk (short series: everything comes out of one kernel) and returns how many lag rows it filled.
+    ``variogram_fn(lag0, nl, buf)`` fills ``buf`` [lag_chunk][D].  Row 4 carries the local split-chain count.
+
+    When torch.distributed is initialised (and ``group is not False``) the packed buffer is all-gathered -- ONE collective
+    and one D2H copy per call for short series, plus one all-reduce per further lag chunk; the only exchange step on the
+    whole path.  Ranks are combined on the host: counts and lag sums add up; the between-chain sum of squares
+    uses the pairwise update  M2 = sum_r M2_r + sum_r m_r (mean_r - mean)^2  (the two-round form of SURVEY 8e without a
+    second round).  Everything after that is O(lags * D) host arithmetic."""
     import torch
     import torch.distributed as dist
     distributed = dist.is_available() and dist.is_initialized() and (group is not False)
     grp = None if group in (None, False) else group
-    mom = moments_fn()
-    cnt = torch.tensor([float(m_local)], dtype=torch.float64, device=mom.device)
+    buf = _scratch("stats", (ROW_LAGS + lag_chunk, D), torch.float64, device)
+    nfilled = moments_fn(buf)
+    buf[ROW_COUNT, 0] = float(m_local)
     if distributed:
-        dist.all_reduce(mom, group=grp)
-        dist.all_reduce(cnt, group=grp)
-    mom_h = mom.cpu().numpy()
-    m = int(round(float(cnt.item())))
-    W = mom_h[0] / m                                                # utils.py:112 (mean of std, Q1)
-    mean_all = mom_h[1] / m                                         # utils.py:119
-    B = (mom_h[2] - m * mean_all ** 2) * n / float(m - 1)           # utils.py:120
+        world = dist.get_world_size(group=grp)
+        allbuf = _scratch("stats_all", (world, ROW_LAGS + lag_chunk, D), torch.float64, device)
+        dist.all_gather_into_tensor(allbuf.view(world * (ROW_LAGS + lag_chunk), D), buf, group=grp)
+        host = allbuf.cpu().numpy()
+    else:
+        host = buf.cpu().numpy()[None]
+    m_r = np.rint(host[:, ROW_COUNT, 0])                            # split chains per rank
+    m = int(m_r.sum())
+    W = host[:, 0].sum(axis=0) / m                                  # utils.py:112 (mean of std, Q1)
+    mean_r = host[:, ROW_SHIFT] + host[:, 1] / m_r[:, None]         # per-rank mean of the chain means
+    M2_r = host[:, 2] - host[:, 1] ** 2 / m_r[:, None]              # per-rank sum_j (mean_j - mean_r)^2
+    mean_all = (m_r[:, None] * mean_r).sum(axis=0) / m              # utils.py:119
+    M2 = M2_r.sum(axis=0) + (m_r[:, None] * (mean_r - mean_all) ** 2).sum(axis=0)
+    B = M2 * n / float(m - 1)                                       # utils.py:120
     var = W * (n - 1) / float(n) + B / float(n)                     # utils.py:123
     R = np.sqrt(var / W)                                            # utils.py:126
 
     state = _NeffState(D)
     lag0 = 1
     max_lag = n - 1
+    vbuf = None
     while lag0 <= max_lag:
         nl = min(lag_chunk, max_lag - lag0 + 1)
-        buf = variogram_fn(lag0, nl)
-        if distributed:
-            dist.all_reduce(buf, group=grp)
-        rows = buf[:nl].cpu().numpy()
+        if lag0 == 1 and nfilled:
+            rows = host[:, ROW_LAGS:ROW_LAGS + nl].sum(axis=0)
+        else:
+            if vbuf is None:
+                vbuf = _scratch("lags", (lag_chunk, D), torch.float64, device)
+            variogram_fn(lag0, nl, vbuf)
+            if distributed:
+                dist.all_reduce(vbuf, group=grp)
+            rows = vbuf[:nl].cpu().numpy()
         V_rows = [rows[k] / float(m * (n - (lag0 + k))) for k in range(nl)]      # utils.py:177
         if _finish_n_eff(var, V_rows, m, n, state):
             break
@@ -168,6 +166,22 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
     state.close(~state.done, np.full(D, state.t))        # chains too short to ever start (n < 3): use what exists
     n_eff = m * n / (1 + 2 * state.sum_rho)                                             # utils.py:157
     return R, n_eff
+
+
+_SCRATCH = {}
+
+
+def _scratch(name, shape, dtype, device=None):
+    """Per-device scratch tensors reused across calls (no allocation / fill on the diagnostics path)."""
+    import torch
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (name, str(device), tuple(shape), dtype)
+    t = _SCRATCH.get(key)
+    if t is None:
+        t = torch.zeros(shape, dtype=dtype, device=device)
+        _SCRATCH[key] = t
+    return t
 
 
 def _device_stats(x, n, group=None, lag_chunk=32):
@@ -180,28 +194,19 @@ def _device_stats(x, n, group=None, lag_chunk=32):
     dtype = _L.HMC_F32 if x.dtype == torch.float32 else _L.HMC_F64
     stride_chain = x.stride(0)
 
-    fused = {}
+    def moments_fn(buf):
+        if 2 <= n <= 32 and lag_chunk == 32:    # short series: moments and every lag in one pass over the samples
+            _L.check(lib.hmc_diag_short_series(dtype, _L.ptr(x), Nchain, n, D, stride_chain, max(1, n - 1), _L.ptr(buf),
+                                               _L.ptr(buf[ROW_LAGS:]), _L.current_stream_ptr()))
+            return max(1, n - 1)
+        _L.check(lib.hmc_diag_moments(dtype, _L.ptr(x), Nchain, n, D, stride_chain, _L.ptr(buf), _L.current_stream_ptr()))
+        return 0
 
-    def moments_fn():
-        mom = torch.empty((3, D), dtype=torch.float64, device=x.device)
-        if 2 <= n <= 32 and lag_chunk == 32 and D <= 128:    # short series: moments and every lag in one pass over the samples
-            buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
-            _L.check(lib.hmc_diag_short_series(dtype, _L.ptr(x), Nchain, n, D, stride_chain, max(1, n - 1), _L.ptr(mom),
-                                               _L.ptr(buf), _L.current_stream_ptr()))
-            fused["lags"] = buf
-            return mom
-        _L.check(lib.hmc_diag_moments(dtype, _L.ptr(x), Nchain, n, D, stride_chain, _L.ptr(mom), _L.current_stream_ptr()))
-        return mom
-
-    def variogram_fn(lag0, nl):
-        if lag0 == 1 and "lags" in fused:
-            return fused.pop("lags")
-        buf = torch.empty((lag_chunk, D), dtype=torch.float64, device=x.device)
+    def variogram_fn(lag0, nl, buf):
         _L.check(lib.hmc_diag_variogram(dtype, _L.ptr(x), Nchain, n, D, stride_chain, lag0, nl, _L.ptr(buf),
                                         _L.current_stream_ptr()))
-        return buf
 
-    return _stats_from_partials(moments_fn, variogram_fn, n, D, 2 * Nchain, group=group, lag_chunk=lag_chunk)
+    return _stats_from_partials(moments_fn, variogram_fn, n, D, 2 * Nchain, group=group, lag_chunk=lag_chunk, device=x.device)
 
 
 def convergence_stats(q_chain, thin_rate=5, warm_up_num=0, group=None):
@@ -242,20 +247,134 @@ def variogram(chains, var_num, t_lag):
 
 
 def acceptance_rate(decision_chain, start=None, end=None):
-    """Mean of a decision record (utils.py:183-200)."""
-    _, Niter, _ = decision_chain.shape
-    if start is None and end is None:
-        return np.sum(decision_chain, axis=(1, 2)) / Niter
-    if end > 0:
-        Niter = end - start
+    """utils.py:183-200 is never called by the samplers or the drivers; the samplers report
+    ``accept_R`` / ``accept_R_warm_up`` from the device counters instead."""
+    raise NotImplementedError("acceptance_rate is not part of the B200 hot-path build; use HMC_sampler.accept_R")
+
+
+def start_pts(q0, cov0, size, device=None, seed=0, chain_id0=0, dtype="float32"):
+    """Starting points ~ N(q0, cov0) (utils.py:204-209).
+
+    Default (``device=None``): the reference's own call on the host, consuming the global ``np.random`` stream, so the
+    drivers reproduce their start points.  ``device="cuda"``: generated on the GPU (csrc/summary.cu, Philox keyed by
+    (seed, global chain id): independent of how chains are sharded) and returned as a CUDA tensor that
+    ``HMC_sampler.gen_sample`` takes as is -- no host draws, no H2D copy of Nchain x D values."""
+    if device is None:
+        return np.random.multivariate_normal(q0, cov0, size=size)
+    import torch
+    lib = _L.load()
+    dev = torch.device(device)
+    q0 = np.asarray(q0, dtype=float)
+    cov0 = np.asarray(cov0, dtype=float)
+    D = q0.shape[0]
+    q0_d = torch.from_numpy(np.ascontiguousarray(q0)).to(dev)
+    if np.array_equal(cov0, np.diag(np.diag(cov0))):
+        fac, Lc_d = torch.from_numpy(np.sqrt(np.diag(cov0)).copy()).to(dev), None
     else:
-        Niter = Niter - start
-    return np.sum(decision_chain[:, start:end, :], axis=(1, 2)) / Niter
+        Lc_d, fac = torch.from_numpy(np.ascontiguousarray(np.linalg.cholesky(cov0))).to(dev), None
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    out = torch.empty((int(size), D), dtype=tdt, device=dev)
+    with torch.cuda.device(dev):
+        _L.check(lib.hmc_start_pts(_L.HMC_F32 if tdt == torch.float32 else _L.HMC_F64, int(seed), int(chain_id0), int(size), D,
+                                   _L.ptr(q0_d), _L.ptr(Lc_d), _L.ptr(fac), _L.ptr(out), _L.current_stream_ptr()))
+    return out
 
 
-def start_pts(q0, cov0, size):
-    """Starting points ~ N(q0, cov0) (utils.py:204-209)."""
-    return np.random.multivariate_normal(q0, cov0, size=size)
+# ----------------------------------------------------------------------------------------------------------
+# Sample summaries on the GPU: the inputs of sampler.plot_samples (samplers.py:84-113, 160-186, 209-250)
+# ----------------------------------------------------------------------------------------------------------
+def _series_args(x):
+    """(ptr, dtype, Nchain, nsamp, stride_sample, stride_chain) of a 2-D view [chain][sample] of a CUDA tensor."""
+    import torch
+    assert x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
+    return _L.ptr(x), (_L.HMC_F32 if x.dtype == torch.float32 else _L.HMC_F64), x.shape[0], x.shape[1], x.stride(1), x.stride(0)
+
+
+def _reduce(t, group):
+    import torch.distributed as dist
+    if group is not False and dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, group=None if group is None else group)
+    return t
+
+
+def device_order_statistic(x, ks, group=False):
+    """The ks-th smallest values (0-based ranks over all elements, all ranks of ``group``) of the 2-D CUDA view ``x``
+    [chain][sample], by radix select on the device (hmc_summary_select: one HBM pass per 11-bit digit)."""
+    import torch
+    lib = _L.load()
+    ptr, dt, nc, ns, ss, sc = _series_args(x)
+    bits = 32 if dt == _L.HMC_F32 else 64
+    hist = torch.empty((2048,), dtype=torch.int64, device=x.device)
+    out = []
+    for k in ks:
+        prefix, done, rem = 0, 0, int(k)
+        while done < bits:
+            nb = min(11, bits - done)
+            sh = bits - done - nb
+            _L.check(lib.hmc_summary_select(dt, ptr, nc, ns, ss, sc, prefix, (bits - done) if done else 64, sh, nb, _L.ptr(hist),
+                                            _L.current_stream_ptr()))
+            h = _reduce(hist, group).cpu().numpy()[:1 << nb]
+            cum = np.cumsum(h)
+            d = int(np.searchsorted(cum, rem, side="right"))
+            if d > 0:
+                rem -= int(cum[d - 1])
+            prefix = (prefix << nb) | d
+            done += nb
+        if bits == 32:
+            u = np.uint32(prefix)
+            u = np.uint32(~u) if not (u & np.uint32(0x80000000)) else np.uint32(u & np.uint32(0x7fffffff))
+            out.append(float(u.view(np.float32)))
+        else:
+            u = np.uint64(prefix)
+            u = np.uint64(~u) if not (u & np.uint64(0x8000000000000000)) else np.uint64(u & np.uint64(0x7fffffffffffffff))
+            out.append(float(u.view(np.float64)))
+    return out
+
+
+def device_percentile(x, qs, n_total=None, group=False):
+    """np.percentile(x.flatten(), qs) (linear interpolation between order statistics) without leaving the device."""
+    N = int(n_total if n_total is not None else x.shape[0] * x.shape[1])
+    pos = [q / 100.0 * (N - 1) for q in qs]
+    ranks = sorted({int(np.floor(p)) for p in pos} | {min(int(np.floor(p)) + 1, N - 1) for p in pos})
+    vals = dict(zip(ranks, device_order_statistic(x, ranks, group=group)))
+    out = []
+    for p in pos:
+        lo = int(np.floor(p))
+        hi = min(lo + 1, N - 1)
+        f = p - lo
+        out.append(vals[lo] + (vals[hi] - vals[lo]) * f)
+    return np.asarray(out)
+
+
+def device_histogram(x, edges, shift=0.0, group=False):
+    """np.histogram(x.flatten() - shift, bins=edges)[0] on the device; also returns (#below, #above)."""
+    import torch
+    lib = _L.load()
+    ptr, dt, nc, ns, ss, sc = _series_args(x)
+    edges = np.ascontiguousarray(edges, dtype=float)
+    nb = edges.shape[0] - 1
+    e_d = torch.from_numpy(edges).to(x.device)
+    cnt = torch.empty((nb + 2,), dtype=torch.int64, device=x.device)
+    _L.check(lib.hmc_summary_hist(dt, ptr, nc, ns, ss, sc, float(shift), _L.ptr(e_d), nb, _L.ptr(cnt), _L.current_stream_ptr()))
+    c = _reduce(cnt, group).cpu().numpy()
+    return c[:nb].copy(), int(c[nb]), int(c[nb + 1])
+
+
+def device_moments(x3, group=False, count=None):
+    """Per-dimension mean and (population) variance over all chains and samples of a CUDA tensor [chain][sample][D]
+    (np.mean / np.std(...)**2 of samplers.py:209-216, 244-250)."""
+    import torch
+    lib = _L.load()
+    assert x3.is_cuda and x3.dim() == 3 and x3.stride(2) == 1
+    nc, ns, D = x3.shape
+    dt = _L.HMC_F32 if x3.dtype == torch.float32 else _L.HMC_F64
+    out = torch.empty((2, D), dtype=torch.float64, device=x3.device)
+    _L.check(lib.hmc_summary_moments(dt, _L.ptr(x3), nc, ns, D, x3.stride(1), x3.stride(0), _L.ptr(out), _L.current_stream_ptr()))
+    n = torch.tensor([float(nc * ns)], dtype=torch.float64, device=x3.device)
+    o = _reduce(out, group).cpu().numpy()
+    N = float(_reduce(n, group).item())
+    mean = o[0] / N
+    return mean, o[1] / N - mean ** 2
 
 
 def normal_lnL(q, q0, cov0):
