@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- leapfrog gradient-evals/sec of the fused HMC trajectory kernel (BASELINE.json metric).
+"""bench.py -- leapfrog gradient-evals/sec (and ESS/sec) of the fused HMC trajectory kernel (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (config.workload = "case3c_65536"): Case 3c of the reference (case3-script.py:136-181): MVN D=100,
-rho=0.95, random trajectory length L in {5..19}, dt=0.1, scaled to 65,536 chains PER GPU (weak scaling:
-chains are independent units, no data-path collective).  A "step" is one launch of the fused
-kernel over one ITERATION BLOCK (50 HMC iterations of every chain, ~12 leapfrog steps each, every iteration
-stored: thin=1, warm-up 0).  Definitions printed with the number:
+Workload (config.workload = "case3c_65536"): Case 3c of the reference (case3-script.py:136-181, README:40-45): MVN D=100,
+rho=0.95, random trajectory length L in {5..19}, dt=0.1, 1000 iterations of which 200 are warm-up, scaled to 65,536
+chains PER GPU (weak scaling: chains are independent units, no data-path collective).  A "step" is ONE SUCH
+RUN: one launch of the fused kernel over all 1000 iterations of every chain (~12 leapfrog steps each; the 801 stored
+samples and energies per chain, 21.8 GB, are the only HBM traffic).  Definitions printed with the number:
   gradient-eval = one full grad U = P (q - mu) for one chain = 2 D^2 = 20,000 flop; value counts the
   leapfrog gradient evaluations sum(L) only (the extra evaluation at the first point of every trajectory is
   NOT counted, but is included in roofline.achieved since the kernel does execute it).
 
 value      : device-timed (CUDA events on the launching stream, barrier + synchronize on both sides, max over
-             ranks), chain state resident in HBM.
-e2e        : the same metric through the public API (samplers.HMC_sampler.gen_sample + compute_convergence_stats)
-             with q_start in pinned HOST memory (H2D inside the timed region) and the diagnostics' result read
-             back to the host (D2H inside); at N>1 the Rhat/ESS moments go through the NCCL all-reduce.
-roofline   : tensor bound: the gradient runs on tcgen05 as an FP32-grade bf16x3 product (6 MMA passes); achieved =
-             executed gradient evals * 2 D^2 / kernel time against the measured dense bf16 peak, with the executed
-             tensor flop (x7.53) and the FP32 FFMA peak measured in this run reported beside it.
+             ranks), start points resident in HBM, every step a fresh run (new Philox seed) into the same output slab.
+e2e        : the same run through the public API (samplers.HMC_sampler.gen_sample + compute_convergence_stats)
+             with q_start in pinned HOST memory (H2D inside the timed region) and the diagnostics' result (Rhat, n_eff per
+             dimension) read back to the host (D2H inside); at N>1 the Rhat/ESS partial sums go through NCCL.  q_chain stays
+             on the device (21 GB per GPU; the host gets it lazily, on attribute access).
+roofline   : tensor bound: the gradient runs on tcgen05 as an FP32-grade split product (fp16x2: 3 MMA passes; bf16x3: 6);
+             achieved = executed gradient evals * 2 D^2 / kernel time against the measured dense bf16 (= fp16) peak, with
+             the executed tensor flop and the FP32 FFMA peak measured in this run reported beside it.
+secondary  : measured in the same run (rank 0 reports; all ranks take part): Case 3d ESS/sec, Case 2c burn-in (262,144 chains
+             over all ranks, Rhat over early windows), NUTS config 4, and the diagnostics kernels' own HBM rooflines.
 cpu_baseline / --impl reference : the oracle port of the reference sampler (oracle/hmc_oracle.py) with the
              reference's own library calls (scipy logpdf for V, np.random.multivariate_normal for p), one
              process per host core, on a bounded sample of the same workload.
@@ -48,7 +51,7 @@ import numpy as np  # noqa: E402
 
 D, RHO, DT, L_LOW, L_HIGH = 100, 0.95, 0.1, 5, 20
 CHAINS_PER_GPU = 65536
-ITER_BLOCK = 50
+NITER, WARM = 1000, 200            # README:40-45 (Case 3c as listed; case3-script.py runs 2000 / 1000)
 METRIC = "leapfrog grad-evals/sec, D=100 rho=0.95 MVN (Case 3c), 65536 chains per B200"
 UNIT = "grad-evals/s"
 
@@ -75,6 +78,7 @@ def _cpu_worker(args):
     q_start = np.random.multivariate_normal(q0, np.diag(np.ones(D)) * 2, size=nchain)
     t0 = time.time()
     R = O.gen_sample_random(D, V, dVdq, q_start, O.NumpyDraws(D), nchain, niter, 1, 0, DT, L_LOW, L_HIGH, record=True)
+    O.convergence_stats(R.q_chain[:, 1:, :], 1, 0)      # the e2e leg of the GPU arm includes the diagnostics: so does this one
     dt = time.time() - t0
     return int(R.L_tape.sum()), dt
 
@@ -177,15 +181,158 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 7700.0, "fallback: nominal 7.7 TB/s (B200_PROFILING.md)"
+
+
+def secondary_measurements(torch, dist, S, U, L, lib, rank, world, dev, log):
+    """Measured in the same run as the headline: every entry says what it is and how it was timed."""
+    out = []
+    hbm, hbm_src = _hbm_peak()
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t.item())
+
+    cov = S.equicorrelated_cov(D, RHO)
+    spec = S.MVNSpec.from_cov(np.zeros(D), cov)
+    Nc = CHAINS_PER_GPU
+    # ---- Case 3d (case3-script-2.py:6-68): L in [50,200): the configuration whose ESS means something --------------------
+    try:
+        def run3d():
+            q0 = U.start_pts(np.zeros(D), 2.0 * np.eye(D), Nc, device=dev, seed=91, chain_id0=rank * Nc)
+            H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=300, thin_rate=1, warm_up_num=100, sampler_type="Random", dt=DT,
+                              L_low=50, L_high=200, dtype="float32", kernel="auto", seed=5, chain_id0=rank * Nc, target=spec,
+                              distributed=(world > 1))
+            H.gen_sample(q0, verbose=False, quiet=True)
+            H.compute_convergence_stats()
+            return H
+        run3d()
+        H, t = timed(run3d)
+        out.append({"name": "case3d_ess", "what": "Case 3d (D=100 rho=0.95, L in [50,200), dt=0.1), %d chains/GPU, 300 iterations, 100 warm-up; "
+                    "start points generated on the device; wall time of gen_sample + compute_convergence_stats" % Nc,
+                    "seconds": t, "kernel_ms": H.kernel_ms, "accept_R": H.accept_R, "grad_evals_per_sec": H.sum_L / t,
+                    "rhat_median": float(np.median(H.R_q)), "rhat_max": float(np.max(H.R_q)),
+                    "n_eff_median": float(np.median(H.n_eff_q)), "n_eff_min": float(np.min(H.n_eff_q)),
+                    "stored_samples": int(world * Nc * 200), "ess_per_stored_sample": float(np.median(H.n_eff_q)) / (world * Nc * 200.0),
+                    "ess_per_sec_median": float(np.median(H.n_eff_q)) / t, "ess_per_sec_min": float(np.min(H.n_eff_q)) / t})
+        del H
+        log("secondary: case3d done")
+    except Exception as exc:
+        out.append({"name": "case3d_ess", "failed": repr(exc)})
+    torch.cuda.empty_cache()
+    # ---- Case 2c (case2-script.py:57-61, 136-195): unit MVN, start ~N(0, 100 I), chain 0 pinned; 262,144 chains over all ranks ----
+    try:
+        tot = 262144
+        Ncl = tot // world
+        spec2 = S.MVNSpec.from_cov(np.zeros(D), np.eye(D))
+
+        def run2c():
+            q0 = U.start_pts(np.zeros(D), 100.0 * np.eye(D), Ncl, device=dev, seed=92, chain_id0=rank * Ncl)
+            if rank == 0:
+                q0[0, :] = 0.0
+                q0[0, 0], q0[0, 1] = 1000.0, -750.0
+            H = S.HMC_sampler(D, None, None, Nchain=Ncl, Niter=200, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=DT,
+                              L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=6, chain_id0=rank * Ncl,
+                              target=spec2, distributed=(world > 1))
+            H.gen_sample(q0, verbose=False, quiet=True)
+            grp = None if world > 1 else False
+            wins = {}
+            for (lo, hi) in ((1, 21), (21, 51), (51, 101), (101, 201)):      # burn-in: Rhat over early windows of stored samples
+                R, _ = U.convergence_stats(H.q_chain_device[:, lo:hi, :], thin_rate=1, warm_up_num=0, group=grp)
+                wins["%d-%d" % (lo, hi - 1)] = {"rhat_median": float(np.median(R)), "rhat_max": float(np.max(R))}
+            return H, wins
+        run2c()
+        (H, wins), t = timed(run2c)
+        out.append({"name": "case2c_burn_in", "what": "Case 2c (unit MVN D=100, start ~N(0,100 I), chain 0 at (1000,-750,0,...)), %d chains over %d GPU(s), "
+                    "200 iterations, L in [5,20); Rhat of windows of stored samples through the all-gather of chain moments" % (tot, world),
+                    "seconds": t, "kernel_ms": H.kernel_ms, "tc_precision": H.tc_precision, "accept_R": H.accept_R,
+                    "grad_evals_per_sec_kernel": H.sum_L / (H.kernel_ms * 1e-3), "rhat_windows": wins})
+        del H
+        log("secondary: case2c done")
+    except Exception as exc:
+        out.append({"name": "case2c_burn_in", "failed": repr(exc)})
+    torch.cuda.empty_cache()
+    # ---- NUTS (BASELINE config 4): D=100 rho=0.95, dt=0.1, d_max=10 ------------------------------------------------------------
+    try:
+        Nn = int(os.environ.get("HMC_BENCH_NUTS_CHAINS", str(Nc)))
+
+        def runnuts():
+            q0 = U.start_pts(np.zeros(D), 2.0 * np.eye(D), Nn, device=dev, seed=93, chain_id0=rank * Nn)
+            H = S.HMC_sampler(D, None, None, Nchain=Nn, Niter=4, sampler_type="NUTS", dt=DT, d_max=10, dtype="float32", seed=7,
+                              chain_id0=rank * Nn, target=spec, on_dmax="stop", distributed=(world > 1))
+            H.gen_sample(q0, verbose=False)
+            return H
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            H, t = timed(runnuts)
+        out.append({"name": "nuts_config4", "what": "NUTS, D=100 rho=0.95, dt=0.1, d_max=10, on_dmax=stop (a chain at depth 10 keeps its live point; "
+                    "the reference would abort the whole run, SURVEY H6), %d chains/GPU, 4 iterations" % Nn,
+                    "seconds": t, "kernel_ms": H.kernel_ms, "leapfrogs": int(H.n_leapfrog_total), "dmax_hits": int(H.n_dmax),
+                    "leapfrogs_per_iteration": H.n_leapfrog_total / float(world * Nn * 4),
+                    "leapfrogs_per_sec": H.n_leapfrog_total / (H.kernel_ms * 1e-3), "kernel": getattr(H, "nuts_kernel", "generic")})
+        del H
+        log("secondary: nuts done")
+    except Exception as exc:
+        out.append({"name": "nuts_config4", "failed": repr(exc)})
+    torch.cuda.empty_cache()
+    # ---- diagnostics kernels on a 6.55 GB float32 stream: algorithmic bytes / kernel time against the measured HBM bandwidth ----
+    if rank == 0:
+        try:
+            x = torch.empty((Nc, 250, D), dtype=torch.float32, device=dev).normal_()
+            xs = torch.empty((Nc, 50, D), dtype=torch.float32, device=dev).normal_()
+            buf = torch.empty((40, D), dtype=torch.float64, device=dev)
+            st = L.current_stream_ptr()
+            cases = [("diag_moments", x, lambda: lib.hmc_diag_moments(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, L.ptr(buf), st), 1.0),
+                     ("diag_variogram_32lags", x, lambda: lib.hmc_diag_variogram(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, 33, 32, L.ptr(buf), st), 2.0),
+                     ("diag_variogram_16lags", x, lambda: lib.hmc_diag_variogram(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, 33, 16, L.ptr(buf), st), 1.0),
+                     ("diag_short_series", xs, lambda: lib.hmc_diag_short_series(L.HMC_F32, L.ptr(xs), Nc, 25, D, 50 * D, 24, L.ptr(buf), L.ptr(buf[5:]), st), 1.0)]
+            for name, arr, fn, passes in cases:
+                for _ in range(2):
+                    L.check(fn())
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    L.check(fn())
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                nbytes = arr.numel() * 4
+                out.append({"name": name, "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                                       "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
+                                                       "algorithmic_bytes": nbytes, "launch_ms": ms, "passes_over_the_stream": passes,
+                                                       "traffic": None}})
+            del x, xs
+            log("secondary: diagnostics kernels done")
+        except Exception as exc:
+            out.append({"name": "diag_kernels", "failed": repr(exc)})
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
-    ap.add_argument("--iter-block", type=int, default=ITER_BLOCK)
+    ap.add_argument("--niter", type=int, default=NITER)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements")
     args = ap.parse_args()
     T0 = time.time()
     rank = int(os.environ.get("RANK", "0"))
@@ -193,11 +340,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(args.warmup, 0)
     K = max(args.steps, 1)
+    Niter = args.niter
+    warm = min(WARM, Niter // 5)
+    Lc = 1 + (Niter - warm)
     config = {"workload": "case3c_65536", "D": D, "rho": RHO, "dt": DT, "L": "[%d,%d)" % (L_LOW, L_HIGH),
-              "chains_per_gpu": args.chains, "iter_block": args.iter_block, "sampler": "Random",
+              "chains_per_gpu": args.chains, "iterations_per_step": Niter, "warm_up": warm, "sampler": "Random",
+              "step": "one Case 3c run: one fused-kernel launch over all iterations of all chains",
               "parallelism": "chains sharded, %d rank(s)" % world,
-              "l2": "state is on-chip; each step streams a fresh %.2f GB output slab per GPU (> 126 MB L2)" %
-                    (args.chains * args.iter_block * (D * 4 + 16) / 1e9)}
+              "l2": "state is on-chip; each step streams a %.2f GB output slab per GPU (> 126 MB L2)" %
+                    (args.chains * Lc * (D * 4 + 16) / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -223,6 +374,7 @@ def main():
     import torch.distributed as dist
     import hmc_b200_lib as L
     import samplers as S
+    import utils as U
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
@@ -249,30 +401,30 @@ def main():
     rng = np.random.RandomState(1234 + rank)
     q_start = (rng.standard_normal((Nc, D)) * np.sqrt(2.0)).astype(np.float32)      # case3-script.py:57-58
 
-    # ---- device-resident leg: one sampler, iteration blocks of ITER_BLOCK, one launch per step ----------------
-    IB = args.iter_block
-    Niter = (W + K) * IB
-    H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random",
+    # ---- device-resident leg: every step = one run (one launch) from the resident start points, new seed, same output slab ----
+    H = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, thin_rate=1, warm_up_num=warm, sampler_type="Random",
                       dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=2026, chain_id0=id0,
                       target=spec)
-    run = H.prepare_random(q_start)               # allocates outputs/state, builds the C-ABI argument block
+    run = H.prepare_random(q_start)               # allocates outputs/state, builds the C-ABI argument block, H2D of q_start
     counters = run["counters"]
+    a = run["args"]
+    a.iter_begin, a.iter_end = 0, Niter
     stream = L.current_stream_ptr()
-    log("buffers ready (%d chains, %d iterations)" % (Nc, Niter))
+    log("buffers ready (%d chains, %d iterations per step)" % (Nc, Niter))
     sampler_thread = ClockSampler(local_rank) if rank == 0 else None      # samples through warm-up + timed region
     if sampler_thread:
         sampler_thread.start()
     for i in range(W):
-        run["args"].iter_begin, run["args"].iter_end = i * IB, (i + 1) * IB
-        L.check(lib.hmc_random_run(run["args"], stream))
+        a.seed = 2026 + i
+        L.check(lib.hmc_random_run(a, stream))
     barrier()
     log("warm-up done")
     c0 = counters.clone()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
-        run["args"].iter_begin, run["args"].iter_end = i * IB, (i + 1) * IB
-        L.check(lib.hmc_random_run(run["args"], stream))
+        a.seed = 2026 + i
+        L.check(lib.hmc_random_run(a, stream))
     ev1.record()
     barrier()
     if sampler_thread:
@@ -281,8 +433,7 @@ def main():
     log("timed region done: %.1f ms for %d steps" % (ms, K))
     dc = (counters - c0).cpu().numpy().astype(np.int64)
     acc_post, sumL = int(dc[1]), int(dc[2])
-    n_traj = Nc * K * IB
-    n_rej = n_traj - acc_post - int(dc[0])
+    n_traj = Nc * K * Niter
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     # the tensor-core kernel evaluates the gradient at the first point of every trajectory too: L + 1 per iteration
     tot = torch.tensor([float(sumL), float(sumL + n_traj)], dtype=torch.float64, device=dev)
@@ -292,10 +443,12 @@ def main():
     ms_max = float(t.item())
     value = float(tot[0].item()) / (ms_max * 1e-3)
     executed_local = float(sumL + n_traj)
+    env_prec = os.environ.get("HMC_B200_TC_PREC", "")[:1]
+    fp16 = env_prec == "f" or (bool(a.flags & L.FLAG_TC_FP16X2) and env_prec != "b")
 
     # ---- roofline of the fused kernel (rank 0's kernel, its own events) ----------------------------------------
-    # The gradient runs on the tensor pipe as six bf16 part products (FP32-grade bf16x3 split) of a 128 x 112 x 112
-    # tile per 128 chain-evaluations: executed tensor flop = 6 * (112/100)^2 = 7.53 x the algorithmic 2 D^2.
+    # The gradient runs on the tensor pipe as NP part products (fp16x2 split: 3, bf16x3 split: 6; both FP32-grade) of a
+    # 128 x 112 x 112 tile per 128 chain-evaluations: executed tensor flop = NP * (112/100)^2 x the algorithmic 2 D^2.
     peak = L.C.c_double(0.0)
     L.check(lib.hmc_ffma_peak(L.C.byref(peak), 0, stream))
     flop = executed_local * 2.0 * D * D
@@ -306,36 +459,42 @@ def main():
     except Exception:
         pass
     bf16_peak = float(peaks.get("bf16_tflops_sustained", 0.0)) or 2250.0
-    tensor_exec = achieved * 6.0 * (112.0 / D) ** 2
-    roofline = {"bound": "tensor", "kernel": "hmc_random_tc_kernel<UDT=true> (tcgen05 bf16x3, 128 chains per CTA)",
+    nprod = 3.0 if fp16 else 6.0
+    tensor_exec = achieved * nprod * (112.0 / D) ** 2
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "tc_kernel_traffic.json")))
+        if tr.get("chains") == Nc and tr.get("niter") == Niter and tr.get("split") == ("fp16x2" if fp16 else "bf16x3"):
+            traffic, traffic_src = float(tr["dram_bytes_per_launch"]), tr.get("source")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "hmc_random_tc_kernel<UDT=true, %s> (tcgen05, 128 chains per CTA)" % ("fp16x2" if fp16 else "bf16x3"),
                 "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; the dense fp16 rate equals the bf16 rate)" if peaks
                                 else "fallback: nominal dense bf16 2250"),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this workload, from the ncu
-                # --set full capture in profiles/r1j_tc_kernel_ncu_summary.csv (0.079 GB read + 1.377 GB written; the
-                # algorithmic stream of stored samples and energies is 1.36 GB)
-                "traffic": 1.455e9 if (Nc == CHAINS_PER_GPU and IB == ITER_BLOCK) else None, "launch_ms": ms / K,
+                "traffic": traffic, "traffic_source": traffic_src or "not captured for this configuration",
+                "algorithmic_bytes": float(Nc) * Lc * (D * 4 + 16), "launch_ms": ms / K,
                 "tensor_tflops_executed": tensor_exec, "frac_executed": tensor_exec / bf16_peak,
                 "fp32_ffma_peak": peak.value / 1e12, "frac_of_fp32_ffma_peak": achieved / (peak.value / 1e12),
                 "note": "achieved = algorithmic flop (executed gradient evals: sum L + one per trajectory start) * 2*D^2 / kernel time; "
-                        "an FP32-grade gradient costs 7.53 bf16 tensor flop per algorithmic flop (tensor_tflops_executed); "
-                        "fp32_ffma_peak is the FFMA microbenchmark of this run (what a CUDA-core kernel is bounded by)"}
+                        "an FP32-grade gradient costs %.2f 16-bit tensor flop per algorithmic flop (tensor_tflops_executed); "
+                        "fp32_ffma_peak is the FFMA microbenchmark of this run (what a CUDA-core kernel is bounded by)" % (nprod * 1.2544)}
 
     # ---- end-to-end leg through the public API, host buffers ----------------------------------------------------
     q_pinned = torch.from_numpy(q_start).pin_memory()
-    del H, run
+    del H, run, a
     torch.cuda.empty_cache()
     e2e_ms = []
     e2e_L = []
     ess = None
-    for i in range(2 + K):
-        H2 = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=IB, thin_rate=1, warm_up_num=0, sampler_type="Random",
+    for i in range(1 + K):
+        H2 = S.HMC_sampler(D, None, None, Nchain=Nc, Niter=Niter, thin_rate=1, warm_up_num=warm, sampler_type="Random",
                            dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=77 + i,
                            chain_id0=id0, target=spec, distributed=(world > 1))
         barrier()
         t0 = time.perf_counter()
         H2.gen_sample(q_pinned, verbose=False, quiet=True)       # H2D of q_start inside
-        H2.compute_convergence_stats()                           # GPU reductions (+ NCCL all-reduce), D2H of R/n_eff
+        H2.compute_convergence_stats()                           # GPU reductions (+ NCCL), D2H of the partial sums
         torch.cuda.synchronize()
         dt_s = time.perf_counter() - t0
         tt = torch.tensor([dt_s], dtype=torch.float64, device=dev)
@@ -343,17 +502,24 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ll)
-        if i >= 2:
+        if i >= 1:
             e2e_ms.append(float(tt.item()) * 1e3)
             e2e_L.append(float(ll.item()))
-            ess = {"n_eff_median": float(np.median(H2.n_eff_q)), "n_eff_min": float(np.min(H2.n_eff_q)),
-                   "rhat_median": float(np.median(H2.R_q)), "stored_samples": int(world * Nc * IB),
-                   "ess_per_sec_median": float(np.median(H2.n_eff_q)) / float(tt.item()), "accept_R": H2.accept_R}
+            ess = {"what": "reference-formula n_eff (utils.py:77-159) of the stored samples of one step's run, over its wall time incl. diagnostics",
+                   "n_eff_median": float(np.median(H2.n_eff_q)), "n_eff_min": float(np.min(H2.n_eff_q)),
+                   "rhat_median": float(np.median(H2.R_q)), "stored_samples": int(world * Nc * (Lc - 1)),
+                   "ess_per_sec_median": float(np.median(H2.n_eff_q)) / float(tt.item()),
+                   "ess_per_sec_min": float(np.min(H2.n_eff_q)) / float(tt.item()), "accept_R": H2.accept_R,
+                   "kernel_ms": H2.kernel_ms}
         del H2
     log("e2e done")
     e2e_value = float(np.sum(e2e_L) / (np.sum(e2e_ms) * 1e-3))
     h2d = Nc * D * 4
-    d2h = 2 * D * 8 + 3 * D * 8 + 32 * D * 8 + 4 * 8
+    d2h = (U.ROW_LAGS + 32) * D * 8 + 16 * 8          # packed statistics buffer + counters; further lag chunks add 32*D*8 each
+
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_measurements(torch, dist, S, U, L, lib, rank, world, dev, log)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -371,9 +537,11 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": sampler_thread.summary() if sampler_thread else None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": float(np.mean(e2e_ms))},
+                        "ms_per_step": float(np.mean(e2e_ms)),
+                        "note": "gen_sample + compute_convergence_stats per step; q_chain (%.1f GB per GPU) stays device-resident and is "
+                                "never copied to the host inside the timed region" % (Nc * Lc * D * 4 / 1e9)},
                 "gpu_launches": K,
-                "roofline": roofline, "cpu_baseline": cpu, "ess": ess,
+                "roofline": roofline, "cpu_baseline": cpu, "ess": ess, "secondary": secondary,
                 "grad_evals_executed_per_sec": float(tot[1].item()) / (ms_max * 1e-3),
                 "reference_unit_steps_per_sec": value * D,
                 "accept_rate": (acc_post + int(dc[0])) / float(n_traj)}

@@ -41,10 +41,13 @@ enum { HMC_F32 = 0, HMC_F64 = 1 };
 
 /* which kernel implements the run */
 enum {
-    HMC_KERNEL_AUTO = 0,    /* tensor-core kernel if it covers the run, else the FFMA2 kernel, else the generic one */
+    HMC_KERNEL_AUTO = 0,    /* tensor-core kernel if it covers the run, else the large-D GEMM path (when a workspace is given), else
+                               the FFMA2 kernel, else the generic one */
     HMC_KERNEL_GENERIC = 1, /* one warp per chain, any D <= 1024, float or double (parity workhorse) */
     HMC_KERNEL_FAST = 2,    /* FP32 FFMA2 register-tile kernel, 20 < D <= 128, identity momentum metric */
-    HMC_KERNEL_TC = 3       /* tcgen05 tensor-core kernel (bf16x3 split, fp32 accumulate in TMEM), D = 100, identity metric */
+    HMC_KERNEL_TC = 3,      /* tcgen05 tensor-core kernel (bf16x3 / fp16x2 split, fp32 accumulate in TMEM), D = 100, identity metric */
+    HMC_KERNEL_BIGD = 4     /* large D (multiple of 256): one tcgen05 GEMM over all chains per leapfrog step, operands by TMA, the
+                               leapfrog update fused into the epilogue; needs hmc_random_args.workspace */
 };
 
 /* hmc_random_args.flags */
@@ -125,9 +128,17 @@ typedef struct hmc_random_args {
     double* phi_q;          /* [N_save_chain0][L_high][2]  rows 0..L of iteration i at [i-1] (samplers.py:444-452) */
     int32_t* phi_len;       /* [N_save_chain0]  L+1 */
     int32_t* decision_chain;/* [N_save_chain0+1] (samplers.py:399, 464) */
+    int32_t store_ring;     /* 0: q_chain / E_chain / dE_chain hold all L_chain stored samples per chain (the reference's layout).
+                               R > 0: they hold R rows per chain and stored sample j goes to row j % R -- a ring of the last R
+                               stored samples for runs whose full stream does not fit (streaming / benchmark use) */
+    int32_t reserved0;
+    void* workspace;        /* scratch of hmc_random_workspace_bytes(args) bytes for HMC_KERNEL_BIGD (1024-byte aligned); NULL otherwise */
+    int64_t workspace_bytes;
 } hmc_random_args;
 
 int hmc_random_run(const hmc_random_args* args, void* cuda_stream);
+/* bytes of hmc_random_args.workspace the large-D path needs for this configuration (0 when it does not apply) */
+int64_t hmc_random_workspace_bytes(const hmc_random_args* args);
 
 /*
  * NUTS sampler: replaces HMC_sampler.gen_sample_NUTS (samplers.py:495-808) and the index helpers

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
         import __graft_entry__ as g
         g.build()
     hdr = open(os.path.join(ROOT, "include", "hmc_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(hmc_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(hmc_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(L.EXPORTS)
     lib = ctypes.CDLL(L.LIB_PATH)
     for name in declared:
@@ -33,12 +33,12 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hmc_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
                    'sizeof(hmc_target),sizeof(hmc_random_args),sizeof(hmc_nuts_args),'
-                   'offsetof(hmc_random_args,decision_chain),offsetof(hmc_nuts_args,n_leapfrog));return 0;}\n')
+                   'offsetof(hmc_random_args,store_ring),offsetof(hmc_nuts_args,n_leapfrog));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
     assert [int(v) for v in out] == [ctypes.sizeof(L.Target), ctypes.sizeof(L.RandomArgs), ctypes.sizeof(L.NutsArgs),
-                                     L.RandomArgs.decision_chain.offset, L.NutsArgs.n_leapfrog.offset]
+                                     L.RandomArgs.store_ring.offset, L.NutsArgs.n_leapfrog.offset]
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -91,7 +91,7 @@ def test_f32_teacher_forced_trajectories(name, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
-@pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small"])
+@pytest.mark.parametrize("name", ["random_case1a", "random_d10_thin3", "random_case3c_small", "random_case2c_small"])
 def test_f32_teacher_forced_decisions(name, kernel):
     if kernel in ("fast", "tc") and name not in FAST_OK:
         pytest.skip("fused kernels: fast covers 20 < D <= 128, tc covers D = 100")

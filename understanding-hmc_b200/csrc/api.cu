@@ -18,6 +18,9 @@ int hmc_random_run_fast(const hmc_random_args& a, cudaStream_t stream);
 bool hmc_random_fast_supported(const hmc_random_args& a, const char** why);
 int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream);
 bool hmc_random_tc_supported(const hmc_random_args& a, const char** why);
+int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream);
+bool hmc_random_bigd_supported(const hmc_random_args& a, const char** why);
+size_t hmc_random_bigd_workspace(const hmc_random_args& a);
 int hmc_nuts_run_generic(const hmc_nuts_args& a, cudaStream_t stream);
 
 extern "C" int hmc_version(void) { return HMC_B200_VERSION; }
@@ -58,7 +61,16 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
     int kernel = a.kernel;
     const char* why = "";
     if (kernel == HMC_KERNEL_AUTO)                  // tensor-core kernel where it applies, then the FFMA kernel, then the generic one
-        kernel = hmc_random_tc_supported(a, &why) ? HMC_KERNEL_TC : hmc_random_fast_supported(a, &why) ? HMC_KERNEL_FAST : HMC_KERNEL_GENERIC;
+        kernel = hmc_random_tc_supported(a, &why) ? HMC_KERNEL_TC
+                 : (a.workspace && hmc_random_bigd_supported(a, &why)) ? HMC_KERNEL_BIGD
+                 : hmc_random_fast_supported(a, &why) ? HMC_KERNEL_FAST : HMC_KERNEL_GENERIC;
+    if (kernel == HMC_KERNEL_BIGD) {
+        if (!hmc_random_bigd_supported(a, &why)) {
+            hmc_set_error("large-D kernel does not cover this configuration: %s", why);
+            return HMC_E_UNSUPPORTED;
+        }
+        return hmc_random_run_bigd(a, stream);
+    }
     if (kernel == HMC_KERNEL_FAST) {
         if (!hmc_random_fast_supported(a, &why)) {
             hmc_set_error("fast kernel does not cover this configuration: %s", why);
@@ -76,6 +88,12 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
     if (kernel == HMC_KERNEL_GENERIC) return hmc_random_run_generic(a, stream);
     hmc_set_error("unknown kernel id %d", a.kernel);
     return HMC_E_BADARG;
+}
+
+extern "C" int64_t hmc_random_workspace_bytes(const hmc_random_args* args) {
+    const char* why = "";
+    if (!args || !hmc_random_bigd_supported(*args, &why)) return 0;
+    return (int64_t)hmc_random_bigd_workspace(*args);
 }
 
 extern "C" int hmc_nuts_run(const hmc_nuts_args* args, void* cuda_stream) {

@@ -366,77 +366,6 @@ __global__ void __launch_bounds__(256, 2) diag_variogram_f32x2_kernel(const floa
     for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
 }
 
-// Short series (n <= NMAX), packed: the n samples of two adjacent dimensions are loaded once, back to back, and the
-// moments and all lag sums are formed from registers (one HBM pass for the whole of utils.convergence_stats).
-template <int NMAX>
-__global__ void __launch_bounds__(128, 3) diag_short_f32x2_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
-                                                                 long stride_chain, int d0, int Dt, int spb, int nlags,
-                                                                 double* __restrict__ mom_out, double* __restrict__ out) {
-    extern __shared__ double sm[];   // [NMAX + 3][Dt]
-    for (int t = threadIdx.x; t < (NMAX + 3) * Dt; t += blockDim.x) sm[t] = 0.0;
-    __syncthreads();
-    const int D2 = Dt >> 1;
-    const int dp = threadIdx.x % D2, sl = threadIdx.x / D2;
-    f32x2 acc[NMAX - 1];
-#pragma unroll
-    for (int k = 0; k < NMAX - 1; ++k) acc[k] = 0ull;
-    double s_std[2] = {0.0, 0.0}, s_mean[2] = {0.0, 0.0}, s_mean2[2] = {0.0, 0.0};
-    double cshift[2] = {0.0, 0.0};               // see diag_moments_kernel
-    if (sl < spb) {
-        cshift[0] = (double)q[d0 + 2 * dp]; cshift[1] = (double)q[d0 + 2 * dp + 1];
-        if (mom_out && blockIdx.x == 0 && sl == 0) { mom_out[3 * D + d0 + 2 * dp] = cshift[0]; mom_out[3 * D + d0 + 2 * dp + 1] = cshift[1]; }
-        const long nseries = 2 * Nchain;
-        const long p2 = pitch >> 1;
-        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
-            const f32x2* x = reinterpret_cast<const f32x2*>(q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0) + dp;
-            f32x2 v[NMAX];
-#pragma unroll
-            for (int i = 0; i < NMAX; ++i) v[i] = (i < n) ? x[(long)i * p2] : 0ull;
-#pragma unroll
-            for (int i = 1; i < NMAX; ++i) {
-                if (i < n) {
-#pragma unroll
-                    for (int k = 0; k < i; ++k) acc[k] = sqacc2(sub2(v[i], v[i - k - 1]), acc[k]);
-                }
-            }
-            if (mom_out) {           // per split chain mean and ddof = 1 standard deviation (utils.py:107-118)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float x0 = c ? hi_of(v[0]) : lo_of(v[0]);
-                    float a = 0.f, b = 0.f;
-#pragma unroll
-                    for (int i = 1; i < NMAX; ++i) {
-                        if (i < n) { const float e = (c ? hi_of(v[i]) : lo_of(v[i])) - x0; a += e; b = fmaf(e, e, b); }
-                    }
-                    const double mean_s = (double)a / (double)n;
-                    double var = ((double)b - (double)n * mean_s * mean_s) / (double)(n - 1);
-                    if (var < 0.0) var = 0.0;
-                    const double mean = mean_s + ((double)x0 - cshift[c]);
-                    s_std[c] += sqrt(var); s_mean[c] += mean; s_mean2[c] += mean * mean;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NMAX - 1; ++k) {
-            if (k < nlags) {
-                atomicAdd(&sm[k * Dt + 2 * dp], (double)lo_of(acc[k]));
-                atomicAdd(&sm[k * Dt + 2 * dp + 1], (double)hi_of(acc[k]));
-            }
-        }
-        if (mom_out) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                atomicAdd(&sm[(NMAX + 0) * Dt + 2 * dp + c], s_std[c]);
-                atomicAdd(&sm[(NMAX + 1) * Dt + 2 * dp + c], s_mean[c]);
-                atomicAdd(&sm[(NMAX + 2) * Dt + 2 * dp + c], s_mean2[c]);
-            }
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
-    if (mom_out) for (int t = threadIdx.x; t < 3 * Dt; t += blockDim.x) atomicAdd(mom_out + (t / Dt) * D + d0 + (t % Dt), sm[NMAX * Dt + t]);
-}
-
 int grid_for(long nseries, int spb, int per_sm = 8) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -509,19 +438,6 @@ static int launch_short_generic(const T* q, int64_t Nchain, int64_t n, int32_t D
     return HMC_OK;
 }
 
-static int launch_short_packed(const float* q, int64_t Nchain, int64_t n, int32_t D, long pitch, int64_t stride_chain, int nlags,
-                               double* mom, double* out, cudaStream_t stream) {
-    constexpr int NL = 32;
-    for (int d0 = 0; d0 < D; d0 += 2 * 128) {
-        const int Dt = (D - d0 < 256) ? D - d0 : 256;
-        const int spb = 128 / (Dt / 2);
-        const size_t smem = sizeof(double) * (NL + 3) * Dt;
-        HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_short_f32x2_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        diag_short_f32x2_kernel<NL><<<grid_for(2 * Nchain, spb, 6), 128, smem, stream>>>(q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, nlags, mom, out);
-    }
-    return HMC_OK;
-}
-
 extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
                                   int32_t lag0, int32_t nlags, double* out, void* cuda_stream) {
     constexpr int NL = 32;
@@ -536,8 +452,7 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
     const bool packed = packed_ok(dtype, q, D, pitch, stride_chain, n);
     if (lag0 == 1 && n <= NL) {                  // short series: one pass, values held in registers
         int rc;
-        if (packed) rc = launch_short_packed((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
-        else if (dtype == HMC_F32) rc = launch_short_generic<float, false>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
+        if (dtype == HMC_F32) rc = launch_short_generic<float, false>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
         else rc = launch_short_generic<double, false>((const double*)q, Nchain, n, D, pitch, stride_chain, nlags, nullptr, out, stream);
         if (rc) return rc;
         HMC_CUDA_CHECK(cudaGetLastError());
@@ -590,8 +505,7 @@ extern "C" int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchai
     HMC_CUDA_CHECK(cudaMemsetAsync(out4xD, 0, sizeof(double) * 4 * D, stream));
     HMC_CUDA_CHECK(cudaMemsetAsync(out_lags, 0, sizeof(double) * nlags * D, stream));
     int rc;
-    if (packed_ok(dtype, q, D, pitch, stride_chain, n)) rc = launch_short_packed((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
-    else if (dtype == HMC_F32) rc = launch_short_generic<float, true>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
+    if (dtype == HMC_F32) rc = launch_short_generic<float, true>((const float*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
     else rc = launch_short_generic<double, true>((const double*)q, Nchain, n, D, pitch, stride_chain, nlags, out4xD, out_lags, stream);
     if (rc) return rc;
     HMC_CUDA_CHECK(cudaGetLastError());

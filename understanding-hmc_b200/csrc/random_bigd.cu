@@ -1,0 +1,666 @@
+// Large-D random-trajectory HMC path (BASELINE config 5: dense-covariance MVN, D = 1024, 131,072 chains per GPU):
+// the gradient of ALL chains, G[Nchain x D] = X[Nchain x D] * F[D x D]^T, is a real dense contraction and runs as a
+// tcgen05 GEMM with TMA-fed operands; the leapfrog update is fused into its epilogue.
+//
+// Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839).
+//
+// One PASS = one gradient evaluation for every chain (per-step GEMM with the leapfrog update fused in):
+//   bigd_gemm_step   persistent CTAs over (128 chains x 256 dimensions) tiles, K = D.  Warp 0 issues the TMA loads
+//                    (cp.async.bulk.tensor, 128-byte swizzle, 2 stages of K = 64), warp 1 issues the tcgen05.mma
+//                    (cta_group::1, kind::f16, M = 128, N = 256, fp32 accumulators double-buffered in the 512 TMEM columns),
+//                    warps 2..5 are the epilogue: tcgen05.ld of the tile, per-chain kick / drift weights by trajectory
+//                    phase (first point: half kick + drift, interior: full kick + drift, last: half kick), momentum and
+//                    position updated in place, the NEXT pass's A operand (the split position) written, partial sums of
+//                    q.g and p.p per (chain, column tile) for the energies.
+//                    FP32-grade product from a two-part fp16 split (x = h1 + h2, F 2^s = f1 + f2; products (1,2) (2,1) (1,1)
+//                    per K step) -- or the three-part bf16 split with six products (flags bit 1 clear).
+//   bigd_events      one thread per chain: trajectory bookkeeping (energies, Metropolis accept on the Philox uniform, step
+//                    counters, samplers.py:434-462); chains whose trajectory ended go on a list.
+//   bigd_trajectory_end  one warp per listed chain: accept (start point <- proposal) or reject (position and operand rows <-
+//                    start point), stored sample row, momentum refresh / new length / new uniform (samplers.py:431, 441,
+//                    461-472), next iteration or chain end.
+// Chains advance asynchronously: every chain has its own phase, the GEMM never waits for a trajectory end.
+// All three kernels of a pass are enqueued back to back; the host looks at the number of running chains every 8 passes.
+//
+// HBM per chain and pass: p and q read + written (16 B / dimension), split position written (4 or 6 B) and read by TMA
+// (4 or 6 B; the four column tiles of a row block re-read it from L2): ~24 B x D vs 2 D^2 x 3 tensor flop.
+#include "hmc_common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+namespace {
+
+constexpr int BM = 128;            // chains per tile (UMMA M)
+constexpr int BN_MAX = 256;        // dimensions per tile (UMMA N; fp32 accumulator columns): 256 for the two-part split, 128 for the three-part one (shared memory)
+constexpr int BK = 64;             // K per stage: 64 16-bit elements = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int EB = 16;             // epilogue column block
+constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+enum : int { MD_IDLE = 0, MD_FIRST = 1, MD_MID = 2, MD_LAST = 3, MD_PENDING = 4 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred pw;\n\tmbarrier.try_wait.parity.shared::cta.b64 pw, [%1], %2;\n\tselp.u32 %0, 1, 0, pw;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major operand tile [rows][64 x 16 bit] written by TMA with the 128-byte swizzle: 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                              // leading byte offset: unused for swizzled K-major (set to 1)
+    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;        // stride byte offset: 8 rows x 128 bytes
+    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// split of a pair of float32 values into 16-bit parts (true signs), NPART = 2: fp16, NPART = 3: bf16
+template <int NPART>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t (&h)[3]) {
+    if constexpr (NPART == 2) {
+        const __half2 a = __floats2half2_rn(x0, x1);
+        const float2 af = __half22float2(a);
+        const __half2 b = __floats2half2_rn(x0 - af.x, x1 - af.y);
+        h[0] = *reinterpret_cast<const uint32_t*>(&a); h[1] = *reinterpret_cast<const uint32_t*>(&b); h[2] = 0u;
+    } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1);
+        float r0 = x0 - __low2float(a), r1 = x1 - __high2float(a);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
+        r0 -= __low2float(b); r1 -= __high2float(b);
+        const __nv_bfloat162 c = __floats2bfloat162_rn(r0, r1);
+        h[0] = *reinterpret_cast<const uint32_t*>(&a); h[1] = *reinterpret_cast<const uint32_t*>(&b); h[2] = *reinterpret_cast<const uint32_t*>(&c);
+    }
+}
+
+struct BigdWs {                      // workspace carved by the host (all device pointers)
+    uint16_t* xp;                    // [NPART][Ncp][D]  split position = A operand of the next pass
+    uint16_t* bp;                    // [NPART][D][D]    split force matrix (x 2^s for the fp16 split) = B operand
+    float* x;                        // [Ncp][D] shifted position q - mu
+    float* x0;                       // [Ncp][D] position at the start of the running trajectory
+    float* p;                        // [Ncp][D] momentum
+    float* red;                      // [Ncp][NT][2] partial (q.g, p.p) per column tile of the last pass
+    int* mode;                       // [Ncp] MD_*
+    int* l;                          // [Ncp] leapfrog steps done in the running trajectory
+    int* L;                          // [Ncp] its length
+    int* it;                         // [Ncp] running iteration
+    int* init;                       // [Ncp] chain start: E_chain[., 0] still to be recorded
+    float* K_new;                    // [Ncp] 0.5 |p|^2 of the momentum of the running iteration
+    float* K0;                       // [Ncp] 0.5 |p|^2 of the chain-start momentum (samplers.py:415)
+    float* lnu;                      // [Ncp] log of the acceptance uniform
+    float* E_init;                   // [Ncp]
+    float* E_prev;                   // [Ncp]
+    int* tile_active;                // [Ncp / 128]
+    int* list;                       // [Ncp] chains whose trajectory ended in this pass (bit 31: accepted)
+    int* counters;                   // [0..1] list length by pass parity, [2] running chains after the last events kernel
+    float binv;                      // 2^-s
+    int Ncp, NT, npart;
+};
+
+template <int NPART, int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                              BigdWs w, int Nchain, int D, const float* __restrict__ dtv) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;                 // one part of one stage
+    constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
+    unsigned char* stage_base = smem;
+    unsigned char* epi = smem + STAGES * STAGE_BYTES;                           // epilogue staging, per warp
+    constexpr int EPI_WARP_BYTES = 2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_BYTES);
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + STAGES;       // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+    const int NT = w.NT, KB = D / BK;
+    const int ntiles = (w.Ncp / BM) * NT;
+    const size_t part_rows_a = (size_t)w.Ncp, part_rows_b = (size_t)D;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int mt = t / NT, nt = t % NT;
+                if (!w.tile_active[mt]) continue;
+                for (int kb = 0; kb < KB; ++kb, ++n) {
+                    const int s = n % STAGES;
+                    mbar_wait(empty + s, ((n / STAGES) & 1) ^ 1);
+                    unsigned char* sb = stage_base + s * STAGE_BYTES;
+                    mbar_expect_tx(full + s, STAGE_BYTES);
+#pragma unroll
+                    for (int pt = 0; pt < NPART; ++pt) {
+                        tma_load_2d(sb + pt * A_BYTES, &mapA, kb * BK, (int)(pt * part_rows_a) + mt * BM, full + s);
+                        tma_load_2d(sb + NPART * A_BYTES + pt * B_BYTES, &mapB, kb * BK, (int)(pt * part_rows_b) + nt * BN, full + s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t fmt = (NPART == 2) ? 0u : 1u;       // 0 = f16, 1 = bf16
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t n = 0, nt_done = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int mt = t / NT;
+                if (!w.tile_active[mt]) continue;
+                const int as = nt_done & 1;
+                mbar_wait(tempty + as, ((nt_done >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t tacc = tmem + (uint32_t)(as * BN);
+                for (int kb = 0; kb < KB; ++kb, ++n) {
+                    const int s = n % STAGES;
+                    mbar_wait(full + s, (n / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t sa = smem_u32(stage_base + s * STAGE_BYTES), sbb = sa + NPART * A_BYTES;
+                    // part products of this K block, small terms first: fp16x2 (1,2) (2,1) (1,1); bf16x3 (1,3) (3,1) (2,2) (1,2) (2,1) (1,1)
+                    constexpr int NPROD = (NPART == 2) ? 3 : 6;
+                    constexpr int pa2[3] = {0, 1, 0}, pb2[3] = {1, 0, 0};
+                    constexpr int pa3[6] = {0, 2, 1, 0, 1, 0}, pb3[6] = {2, 0, 1, 1, 0, 0};
+#pragma unroll
+                    for (int pr = 0; pr < NPROD; ++pr) {
+                        const int pa = (NPART == 2) ? pa2[pr % 3] : pa3[pr], pb = (NPART == 2) ? pb2[pr % 3] : pb3[pr];
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t ad = make_desc_sw128(sa + pa * A_BYTES + k * 32);
+                            const uint64_t bd = make_desc_sw128(sbb + pb * B_BYTES + k * 32);
+                            umma_ss(tacc, ad, bd, idesc, (kb | pr | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty + s);                   // frees the stage when these MMAs are done
+                }
+                umma_commit(tfull + as);                      // accumulator complete
+                ++nt_done;
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 = chains of the tile =====
+        const int quarter = warp & 3;
+        float* Ps = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);     // [32][EB + 1]
+        float* Xs = Ps + 32 * (EB + 1) + 16;                                        // [32][EB + 1] (16 words on: other banks than Ps)
+        uint32_t* Hs = reinterpret_cast<uint32_t*>(Xs + 32 * (EB + 1));            // [NPART][32][EB / 2 + 1]
+        uint32_t nt_done = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int mt = t / NT, nt = t % NT;
+            if (!w.tile_active[mt]) continue;
+            const int as = nt_done & 1;
+            const long row0 = (long)mt * BM + quarter * 32;          // first chain of this warp
+            const long chain = row0 + lane;
+            const int md = (chain < Nchain) ? w.mode[chain] : MD_IDLE;
+            const float kw = (md == MD_MID) ? -w.binv : ((md == MD_FIRST || md == MD_LAST) ? -0.5f * w.binv : 0.f);
+            const float dw = (md == MD_FIRST || md == MD_MID) ? 1.f : 0.f;
+            const bool live = __any_sync(HMC_FULL_MASK, md == MD_FIRST || md == MD_MID || md == MD_LAST);
+            mbar_wait(tfull + as, (nt_done >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            float hv = 0.f, hk = 0.f;
+            if (live) {
+                for (int cb = 0; cb < BN / EB; ++cb) {
+                    const int c0 = nt * BN + cb * EB;
+                    // coalesced rows -> shared (lanes 0..15: momentum, lanes 16..31: position)
+                    {
+                        const float* src = (lane < 16 ? w.p : w.x) + c0 + (lane & 15);
+                        float* dst = (lane < 16 ? Ps : Xs) + (lane & 15);
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) dst[i * (EB + 1)] = src[(size_t)(row0 + i) * D];
+                    }
+                    __syncwarp();
+                    uint32_t gv[16];
+                    tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cb * EB), gv);
+                    float xn[EB];
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) {
+                        const float g = __uint_as_float(gv[j]);
+                        const float dtj = __ldg(dtv + c0 + j);
+                        const float xo = Xs[lane * (EB + 1) + j];
+                        hv = fmaf(xo, g, hv);
+                        const float pn = fmaf(g, kw * dtj, Ps[lane * (EB + 1) + j]);       // samplers.py:835, 837
+                        hk = fmaf(pn, pn, hk);
+                        xn[j] = fmaf(pn, dw * dtj, xo);                                   // samplers.py:836
+                        Ps[lane * (EB + 1) + j] = pn;
+                        Xs[lane * (EB + 1) + j] = xn[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < EB / 2; ++j) {
+                        uint32_t h[3];
+                        split_pair<NPART>(xn[2 * j], xn[2 * j + 1], h);
+#pragma unroll
+                        for (int pt = 0; pt < NPART; ++pt) Hs[(pt * 32 + lane) * (EB / 2 + 1) + j] = h[pt];
+                    }
+                    __syncwarp();
+                    // shared -> coalesced rows
+                    {
+                        float* dst = (lane < 16 ? w.p : w.x) + c0 + (lane & 15);
+                        const float* src = (lane < 16 ? Ps : Xs) + (lane & 15);
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) dst[(size_t)(row0 + i) * D] = src[i * (EB + 1)];
+                    }
+#pragma unroll
+                    for (int pt = 0; pt < NPART; ++pt) {
+                        // 8 words per row and part: lanes 8 r .. 8 r + 7 store row i + r (four rows per instruction)
+                        uint32_t* dstp = reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp) * D) + (c0 >> 1) + (lane & 7);
+#pragma unroll 4
+                        for (int i = 0; i < 32; i += 4) {
+                            const int r = i + (lane >> 3);
+                            dstp[(size_t)(row0 + r) * (D >> 1)] = Hs[(pt * 32 + r) * (EB / 2 + 1) + (lane & 7)];
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (chain < Nchain) { w.red[((size_t)chain * NT + nt) * 2] = hv; w.red[((size_t)chain * NT + nt) * 2 + 1] = hk; }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + as);
+            ++nt_done;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// momentum draw for one chain by one warp: p row, 0.5 |p|^2, and (iteration >= 1) trajectory length and log-uniform
+// (same Philox keying as every other kernel: hmc_normal4 / hmc_scalar_draws)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bigd_draw(const hmc_random_args& a, long m, int iter, int lane, float* prow, int* L, float* lnu) {
+    const int D = a.target.D;
+    const uint64_t gid = (uint64_t)(a.chain_id0 + m);
+    float s = 0.f;
+    if (a.p_tape) {
+        const double* src = a.p_tape + ((size_t)m * (a.Niter + 1) + iter) * D;
+        for (int j = lane; j < D; j += 32) { const float v = (float)src[j]; if (prow) prow[j] = v; s = fmaf(v, v, s); }
+        if (iter >= 1) { *L = a.L_tape[(size_t)m * a.Niter + iter - 1]; *lnu = (float)log(a.u_tape[(size_t)m * a.Niter + iter - 1]); }
+    } else {
+        for (int sl = lane; sl < D / 4; sl += 32) {
+            const float4 z = hmc_normal4(a.seed, gid, (uint32_t)iter, (uint32_t)sl);
+            if (prow) *reinterpret_cast<float4*>(prow + 4 * sl) = z;
+            s += z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
+        }
+        if (iter >= 1) { double u; hmc_scalar_draws(a.seed, gid, (uint32_t)iter, a.L_low, a.L_high, L, &u); *lnu = (float)log(u); }
+    }
+    return 0.5f * warp_sum<float>(s);
+}
+
+template <int NPART>
+__device__ __forceinline__ void bigd_write_parts(const BigdWs& w, long m, int D, int lane, const float* xrow) {
+    for (int j = 2 * lane; j < D; j += 64) {
+        uint32_t h[3];
+        split_pair<NPART>(xrow[j], xrow[j + 1], h);
+#pragma unroll
+        for (int pt = 0; pt < NPART; ++pt) reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp + m) * D)[j >> 1] = h[pt];
+    }
+}
+
+// chain start (samplers.py:411-420) or resume from state_q: one warp per chain
+template <int NPART>
+__global__ void __launch_bounds__(128) bigd_init(hmc_random_args a, BigdWs w) {
+    const int lane = threadIdx.x & 31, D = a.target.D;
+    const long m = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (m >= w.Ncp) return;
+    float* xr = w.x + (size_t)m * D;
+    float* x0r = w.x0 + (size_t)m * D;
+    float* pr = w.p + (size_t)m * D;
+    if (m >= a.Nchain) {                                     // padding rows of the last tile
+        for (int j = lane; j < D; j += 32) { xr[j] = 0.f; x0r[j] = 0.f; pr[j] = 0.f; }
+        bigd_write_parts<NPART>(w, m, D, lane, xr);
+        if (lane == 0) { w.mode[m] = MD_IDLE; w.it[m] = a.iter_end + 1; }
+        return;
+    }
+    const bool fresh = a.iter_begin == 0;
+    const float* src = (fresh ? (const float*)a.q_start : (const float*)a.state_q) + (size_t)m * D;
+    const float* mu = (const float*)a.target.mu;
+    const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;
+    for (int j = lane; j < D; j += 32) {
+        const float v = src[j];
+        if (fresh) ((float*)a.q_chain)[(size_t)m * Lrow * D + j] = v;              // samplers.py:413
+        xr[j] = v - mu[j]; x0r[j] = v - mu[j];
+    }
+    __syncwarp();
+    bigd_write_parts<NPART>(w, m, D, lane, xr);
+    int L = 1; float lnu = 0.f;
+    float K0 = 0.f;
+    if (fresh) K0 = bigd_draw(a, m, 0, lane, nullptr, &L, &lnu);                   // samplers.py:415 (K only)
+    const int it = a.iter_begin + 1;
+    const float Kn = bigd_draw(a, m, it, lane, pr, &L, &lnu);                      // samplers.py:431, 441, 461
+    if (lane == 0) {
+        w.mode[m] = (it <= a.iter_end) ? MD_FIRST : MD_IDLE;
+        w.l[m] = 0; w.L[m] = L; w.it[m] = it; w.init[m] = fresh ? 1 : 0;
+        w.K_new[m] = Kn; w.K0[m] = K0; w.lnu[m] = lnu;
+        w.E_init[m] = 0.f; w.E_prev[m] = fresh ? 0.f : (float)a.state_eprev[m];
+        if (fresh && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
+    }
+}
+
+// per-chain bookkeeping after a pass (one thread per chain, one block per 128-chain tile)
+__global__ void __launch_bounds__(BM) bigd_events(hmc_random_args a, BigdWs w, int pass) {
+    const long m = (long)blockIdx.x * BM + threadIdx.x;
+    const int D = a.target.D;
+    const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;
+    if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[(pass + 1) & 1] = 0;       // list length of the NEXT pass
+    int md = (m < a.Nchain) ? w.mode[m] : MD_IDLE;
+    unsigned long long acc_warm = 0, acc_post = 0, sL = 0, sL2 = 0;
+    if (md == MD_FIRST || md == MD_MID || md == MD_LAST) {
+        float hv = 0.f, hk = 0.f;
+        for (int t = 0; t < w.NT; ++t) { hv += w.red[((size_t)m * w.NT + t) * 2]; hk += w.red[((size_t)m * w.NT + t) * 2 + 1]; }
+        const float V = fmaf(0.5f * w.binv, hv, (float)a.target.v_const);           // V(q) at the point the gradient was taken
+        const int it = w.it[m];
+        const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
+        const float* mu = (const float*)a.target.mu;
+        if (md == MD_FIRST) {
+            const int L = w.L[m];
+            sL = (unsigned long long)L; sL2 = (unsigned long long)L * L;
+            if (w.init[m]) {                                                        // samplers.py:416-420
+                const float E0 = V + w.K0[m];
+                a.E_chain[(size_t)m * Lrow] = (double)E0; a.dE_chain[(size_t)m * Lrow] = 0.0;
+                w.E_prev[m] = E0; w.init[m] = 0;
+            }
+            const float Ei = V + w.K_new[m];                                        // samplers.py:434-438
+            w.E_init[m] = Ei;
+            if (it >= a.warm_up_num) {
+                const long idx = ((it - a.warm_up_num) / a.thin_rate) % Lrow;
+                a.E_chain[(size_t)m * Lrow + idx] = (double)Ei;
+                a.dE_chain[(size_t)m * Lrow + idx] = (double)(Ei - w.E_prev[m]);
+            }
+            if (tr) {                                                               // samplers.py:442-452
+                a.phi_len[it - 1] = L + 1;
+                double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;
+                phi[0] = (double)(w.x0[(size_t)m * D] + mu[0]); phi[1] = (double)(w.x0[(size_t)m * D + 1] + mu[1]);
+                phi[2] = (double)(w.x[(size_t)m * D] + mu[0]); phi[3] = (double)(w.x[(size_t)m * D + 1] + mu[1]);
+            }
+            w.l[m] = 1;
+            md = (L == 1) ? MD_LAST : MD_MID;
+        } else if (md == MD_MID) {
+            const int l = w.l[m] + 1;
+            if (tr) {
+                double* phi = a.phi_q + (size_t)(it - 1) * a.L_high * 2;
+                phi[2 * l] = (double)(w.x[(size_t)m * D] + mu[0]); phi[2 * l + 1] = (double)(w.x[(size_t)m * D + 1] + mu[1]);
+            }
+            w.l[m] = l;
+            if (l == w.L[m]) md = MD_LAST;
+        } else {                                                                    // Metropolis accept (samplers.py:455-472)
+            const float Ei = w.E_init[m];
+            const float dE = (V + 0.5f * hk) - Ei;
+            w.E_prev[m] = Ei;                                                       // samplers.py:460
+            const bool accepted = (dE < 0.f) || (w.lnu[m] < -dE);                   // samplers.py:462
+            if (accepted) { if (it >= a.warm_up_num) acc_post = 1; else acc_warm = 1; }
+            if (tr) a.decision_chain[it - 1] = accepted ? 1 : 0;
+            const int slot = atomicAdd(&w.counters[pass & 1], 1);
+            w.list[slot] = (int)m | (accepted ? (1 << 31) : 0);
+            md = MD_PENDING;
+        }
+        w.mode[m] = md;
+    }
+    const int running = __syncthreads_count(md != MD_IDLE);
+    if (threadIdx.x == 0) {
+        w.tile_active[blockIdx.x] = running > 0;
+        if (running) atomicAdd(&w.counters[2], running);
+    }
+    if (a.counters) {
+        const unsigned long long c0 = warp_sum<unsigned long long>(acc_warm), c1 = warp_sum<unsigned long long>(acc_post);
+        const unsigned long long c2 = warp_sum<unsigned long long>(sL), c3 = warp_sum<unsigned long long>(sL2);
+        if ((threadIdx.x & 31) == 0 && (c0 | c1 | c2 | c3)) {
+            if (c0) atomicAdd(a.counters + 0, c0);
+            if (c1) atomicAdd(a.counters + 1, c1);
+            atomicAdd(a.counters + 2, c2); atomicAdd(a.counters + 3, c3);
+        }
+    }
+}
+
+// trajectory ends: one warp per listed chain
+template <int NPART>
+__global__ void __launch_bounds__(256) bigd_trajectory_end(hmc_random_args a, BigdWs w, int pass) {
+    const int lane = threadIdx.x & 31, D = a.target.D;
+    const int n = w.counters[pass & 1];
+    const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;
+    const float* mu = (const float*)a.target.mu;
+    for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
+        const int ent = w.list[e];
+        const long m = ent & 0x7fffffff;
+        const bool accepted = ent < 0;
+        float* xr = w.x + (size_t)m * D;
+        float* x0r = w.x0 + (size_t)m * D;
+        int it = w.it[m];
+        const bool keep = it >= a.warm_up_num;
+        float* dst = keep ? (float*)a.q_chain + ((size_t)m * Lrow + ((it - a.warm_up_num) / a.thin_rate) % Lrow) * D : nullptr;
+        const bool last = it >= a.iter_end;
+        float* sq = last ? (float*)a.state_q + (size_t)m * D : nullptr;
+        if (accepted) {                                                             // samplers.py:463-469
+            for (int j = 4 * lane; j < D; j += 128) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + j);
+                *reinterpret_cast<float4*>(x0r + j) = v;
+                const float4 mu4 = *reinterpret_cast<const float4*>(mu + j);
+                const float4 q = make_float4(v.x + mu4.x, v.y + mu4.y, v.z + mu4.z, v.w + mu4.w);
+                if (dst) *reinterpret_cast<float4*>(dst + j) = q;
+                if (sq) *reinterpret_cast<float4*>(sq + j) = q;
+            }
+        } else {                                                                    // samplers.py:470-472
+            for (int j = 4 * lane; j < D; j += 128) {
+                const float4 v = *reinterpret_cast<const float4*>(x0r + j);
+                *reinterpret_cast<float4*>(xr + j) = v;
+                const float4 mu4 = *reinterpret_cast<const float4*>(mu + j);
+                const float4 q = make_float4(v.x + mu4.x, v.y + mu4.y, v.z + mu4.z, v.w + mu4.w);
+                if (dst) *reinterpret_cast<float4*>(dst + j) = q;
+                if (sq) *reinterpret_cast<float4*>(sq + j) = q;
+            }
+            __syncwarp();
+            bigd_write_parts<NPART>(w, m, D, lane, x0r);
+        }
+        if (last) {
+            if (lane == 0) { w.mode[m] = MD_IDLE; w.it[m] = it + 1; a.state_eprev[m] = (double)w.E_prev[m]; }
+        } else {
+            it += 1;
+            int L = 1; float lnu = 0.f;
+            const float Kn = bigd_draw(a, m, it, lane, w.p + (size_t)m * D, &L, &lnu);      // samplers.py:431, 441, 461
+            if (lane == 0) { w.K_new[m] = Kn; w.L[m] = L; w.lnu[m] = lnu; w.l[m] = 0; w.it[m] = it; w.mode[m] = MD_FIRST; }
+        }
+    }
+}
+
+// force matrix -> split 16-bit parts, K-major rows: bp[part][n][k] = part(F[n][k] * scale); Ft[k][n] = F[n][k]
+template <int NPART>
+__global__ void bigd_split_matrix(const float* __restrict__ Ft, int D, int Dpad, float scale, uint16_t* __restrict__ bp) {
+    const long total = (long)D * (D / 2);
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int n = (int)(t / (D / 2)), k = 2 * (int)(t % (D / 2));
+        uint32_t h[3];
+        split_pair<NPART>(Ft[(size_t)k * Dpad + n] * scale, Ft[(size_t)(k + 1) * Dpad + n] * scale, h);
+#pragma unroll
+        for (int pt = 0; pt < NPART; ++pt) reinterpret_cast<uint32_t*>(bp + ((size_t)pt * D + n) * D)[k >> 1] = h[pt];
+    }
+}
+
+__global__ void bigd_absmax(const float* __restrict__ Ft, int D, int Dpad, unsigned int* out) {
+    unsigned int mx = 0u;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < (long)D * D; t += (long)gridDim.x * blockDim.x)
+        mx = max(mx, __float_as_uint(fabsf(Ft[(size_t)(t / D) * Dpad + (t % D)])));
+    mx = __reduce_max_sync(HMC_FULL_MASK, mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D map over a [rows][D] matrix of 16-bit elements, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, bool f16, void* base, uint64_t rows, uint64_t D, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { hmc_set_error("cuTensorMapEncodeTiled is not available from the driver"); return HMC_E_CUDA; }
+    const cuuint64_t dims[2] = {D, rows};
+    const cuuint64_t strides[1] = {D * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hmc_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return HMC_E_CUDA; }
+    return HMC_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carve the workspace; returns the bytes needed (ws may be NULL to only size it)
+size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn) {
+    const long Ncp = (Nchain + BM - 1) / BM * BM;
+    const int NT = D / bn;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = ws ? ws + off : nullptr; off = align_up(off + bytes, 1024); return p; };
+    w.Ncp = (int)Ncp; w.NT = NT; w.npart = npart;
+    w.xp = (uint16_t*)take((size_t)npart * Ncp * D * 2);
+    w.bp = (uint16_t*)take((size_t)npart * D * D * 2);
+    w.x = (float*)take((size_t)Ncp * D * 4);
+    w.x0 = (float*)take((size_t)Ncp * D * 4);
+    w.p = (float*)take((size_t)Ncp * D * 4);
+    w.red = (float*)take((size_t)Ncp * NT * 2 * 4);
+    w.mode = (int*)take(Ncp * 4); w.l = (int*)take(Ncp * 4); w.L = (int*)take(Ncp * 4); w.it = (int*)take(Ncp * 4); w.init = (int*)take(Ncp * 4);
+    w.K_new = (float*)take(Ncp * 4); w.K0 = (float*)take(Ncp * 4); w.lnu = (float*)take(Ncp * 4); w.E_init = (float*)take(Ncp * 4);
+    w.E_prev = (float*)take(Ncp * 4);
+    w.tile_active = (int*)take((Ncp / BM) * 4);
+    w.list = (int*)take(Ncp * 4);
+    w.counters = (int*)take(64);
+    return off;
+}
+
+template <int NPART, int BN>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + 4 * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 16 * 8 + 64;
+}
+static_assert(gemm_smem_bytes<2, 256>() <= 232448 && gemm_smem_bytes<3, 128>() <= 232448, "shared memory of the large-D GEMM exceeds 227 KB");
+
+template <int NPART, int BN>
+int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
+    const int D = a.target.D;
+    BigdWs w;
+    const size_t need = carve(w, (unsigned char*)a.workspace, a.Nchain, D, NPART, BN);
+    if (!a.workspace || (size_t)a.workspace_bytes < need) {
+        hmc_set_error("large-D kernel needs a workspace of %zu bytes (hmc_random_workspace_bytes)", need);
+        return HMC_E_BADARG;
+    }
+    int dev = 0, sms = 0;
+    HMC_CUDA_CHECK(cudaGetDevice(&dev));
+    HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // force matrix parts (scaled to the top of the fp16 range for the fp16 split)
+    float scale = 1.f;
+    HMC_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, 64, stream));
+    if (NPART == 2) {
+        unsigned int* mxd = (unsigned int*)(w.counters + 8);
+        bigd_absmax<<<sms * 4, 256, 0, stream>>>((const float*)a.target.Ft, D, a.target.D_pad, mxd);
+        unsigned int mx = 0;
+        HMC_CUDA_CHECK(cudaMemcpyAsync(&mx, mxd, 4, cudaMemcpyDeviceToHost, stream));
+        HMC_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const int e = (int)(mx >> 23) - 127;
+        int sft = (mx == 0u || e < -100) ? 0 : 14 - e;
+        sft = sft > 100 ? 100 : (sft < -100 ? -100 : sft);
+        scale = ldexpf(1.f, sft);
+    }
+    w.binv = 1.f / scale;
+    bigd_split_matrix<NPART><<<sms * 8, 256, 0, stream>>>((const float*)a.target.Ft, D, a.target.D_pad, scale, w.bp);
+    CUtensorMap mapA, mapB;
+    if (int rc = make_map(&mapA, NPART == 2, w.xp, (uint64_t)NPART * w.Ncp, D, BM)) return rc;
+    if (int rc = make_map(&mapB, NPART == 2, w.bp, (uint64_t)NPART * D, D, BN)) return rc;
+    bigd_init<NPART><<<(w.Ncp + 3) / 4, 128, 0, stream>>>(a, w);
+    const int ntile_rows = w.Ncp / BM;
+    HMC_CUDA_CHECK(cudaMemsetAsync(w.tile_active, 0xff, (size_t)ntile_rows * 4, stream));
+    const size_t smem = gemm_smem_bytes<NPART, BN>();
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(bigd_gemm_step<NPART, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = ntile_rows * w.NT;
+    const int grid = ntiles < sms ? ntiles : sms;
+    int* running_h = nullptr;
+    HMC_CUDA_CHECK(cudaMallocHost(&running_h, 4));
+    const long max_pass = (long)(a.iter_end - a.iter_begin) * (a.L_high + 1) + 8;
+    int rc = HMC_OK;
+    for (long pass = 0; pass < max_pass; ++pass) {
+        bigd_gemm_step<NPART, BN><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, w, a.Nchain, D, (const float*)a.target.dt);
+        cudaMemsetAsync(w.counters + 2, 0, 4, stream);
+        bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
+        bigd_trajectory_end<NPART><<<sms * 2, 256, 0, stream>>>(a, w, (int)pass);
+        if ((pass & 7) == 7) {
+            // chains that ended their last trajectory in this pass are still MD_PENDING for the events kernel's count: they are
+            // counted as running and found idle at the next look
+            if (cudaMemcpyAsync(running_h, w.counters + 2, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess) { rc = HMC_E_CUDA; break; }
+            if (*running_h == 0) break;
+        }
+    }
+    cudaFreeHost(running_h);
+    if (rc == HMC_OK) HMC_CUDA_CHECK(cudaGetLastError());
+    else hmc_set_error("large-D kernel: CUDA error in the pass loop: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+}  // namespace
+
+bool hmc_random_bigd_supported(const hmc_random_args& a, const char** why) {
+    if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
+    if (a.target.Mit || a.target.Pt || a.target.Lct) { *why = "identity momentum metric only"; return false; }
+    if (a.target.D < BN_MAX || (a.target.D % BN_MAX) != 0 || a.target.D > 8192) { *why = "D must be a multiple of 256 in [256, 8192]"; return false; }
+    if (a.iter_end <= a.iter_begin) { *why = "needs at least one iteration"; return false; }
+    return true;
+}
+
+size_t hmc_random_bigd_workspace(const hmc_random_args& a) {
+    BigdWs w;                                     // sized for the larger of the two variants
+    return carve(w, nullptr, a.Nchain, a.target.D, 3, 128);
+}
+
+int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream) {
+    bool fp16 = (a.flags & HMC_FLAG_TC_FP16X2) != 0;
+    if (const char* e = getenv("HMC_B200_TC_PREC")) fp16 = (e[0] == 'f');
+    return fp16 ? run_bigd<2, 256>(a, stream) : run_bigd<3, 128>(a, stream);
+}

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
     const int cg = active ? lane / NDG : 0;
     const int dg = active ? lane % NDG : 0;
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;         // rows allocated per chain (ring of the last store_ring stored samples)
     float* q_chain = (float*)a.q_chain;
     const float dt0 = dt_s[0];
 
@@ -218,9 +219,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                 // ---- the trajectory of iteration `it` ended: keep or restore the position, store the sample
                 //      (samplers.py:462-472)
                 const bool keep = it >= a.warm_up_num;
-                const long idx = keep ? (it - a.warm_up_num) / a.thin_rate : 0;
+                const long idx = keep ? ((it - a.warm_up_num) / a.thin_rate) % Lrow : 0;
                 if (owner) {
-                    float* dst = q_chain + ((size_t)m * Lc + idx) * D;
+                    float* dst = q_chain + ((size_t)m * Lrow + idx) * D;
                     float* q0 = q0g + (size_t)m * D;
 #pragma unroll
                     for (int jj = 0; jj < TN; ++jj) {
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                             if (a.iter_begin == 0) {
                                 qv = ((const float*)a.q_start)[(size_t)m * D + j];
                                 q0[j] = qv;
-                                q_chain[(size_t)m * Lc * D + j] = qv;                       // samplers.py:413
+                                q_chain[(size_t)m * Lrow * D + j] = qv;                       // samplers.py:413
                             } else {
                                 qv = q0[j];
                             }
@@ -312,9 +313,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     // E_initial of the new iteration (samplers.py:434-438): V at the accepted point + new kinetic energy
                     b.Einit = b.V + (double)b.Knew;
                     if (itn >= a.warm_up_num) {
-                        const long idx = (itn - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)m * Lc + idx] = b.Einit;
-                        a.dE_chain[(size_t)m * Lc + idx] = b.Einit - b.Eprev;
+                        const long idx = ((itn - a.warm_up_num) / a.thin_rate) % Lrow;
+                        a.E_chain[(size_t)m * Lrow + idx] = b.Einit;
+                        a.dE_chain[(size_t)m * Lrow + idx] = b.Einit - b.Eprev;
                     }
                     b.l = 1;
                 } else {
@@ -506,16 +507,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     // first point of a trajectory reached through a fresh gradient (chain start or after a rejection)
                     if (b.init) {                                      // samplers.py:416-420
                         const double E0 = V + (double)b.K0;
-                        a.E_chain[(size_t)b.m * Lc] = E0;
-                        a.dE_chain[(size_t)b.m * Lc] = 0.0;
+                        a.E_chain[(size_t)b.m * Lrow] = E0;
+                        a.dE_chain[(size_t)b.m * Lrow] = 0.0;
                         b.Eprev = E0;
                         b.init = 0;
                     }
                     b.Einit = V + (double)b.Knew;                      // samplers.py:434-438
                     if (b.it >= a.warm_up_num) {
-                        const long idx = (b.it - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)b.m * Lc + idx] = b.Einit;
-                        a.dE_chain[(size_t)b.m * Lc + idx] = b.Einit - b.Eprev;
+                        const long idx = ((b.it - a.warm_up_num) / a.thin_rate) % Lrow;
+                        a.E_chain[(size_t)b.m * Lrow + idx] = b.Einit;
+                        a.dE_chain[(size_t)b.m * Lrow + idx] = b.Einit - b.Eprev;
                     }
                     b.l = 1;
                     if (tr) {

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     const T* dt_g = (const T*)a.target.dt;
     T* q_chain = (T*)a.q_chain;
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;   // samplers.py:31
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;         // rows allocated per chain (ring of the last store_ring stored samples)
 
     T q[NJ], p[NJ], f[NJ], d[NJ], mu[NJ], dt[NJ], tmp[NJ];
 #pragma unroll
@@ -86,11 +87,11 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
     if (a.iter_begin == 0) {                                            // samplers.py:413-420
         const T* qs = (const T*)a.q_start + (size_t)m * D;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lc * D + j] = q[i]; } }
+        for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) { q[i] = qs[j]; q_chain[(size_t)m * Lrow * D + j] = q[i]; } }
         draw_p(0);
         force();
         const double E0 = potential() + kinetic();
-        if (lane == 0) { a.E_chain[(size_t)m * Lc] = E0; a.dE_chain[(size_t)m * Lc] = 0.0; }
+        if (lane == 0) { a.E_chain[(size_t)m * Lrow] = E0; a.dE_chain[(size_t)m * Lrow] = 0.0; }
         E_previous = E0;
         if (a.decision_chain && gid == 0 && lane == 0) a.decision_chain[a.N_save_chain0] = 0;
     } else {
@@ -108,10 +109,10 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
         force();
         const double E_initial = potential() + kinetic();               // samplers.py:434
         const bool keep = it >= a.warm_up_num;
-        const long idx = keep ? (it - a.warm_up_num) / a.thin_rate : 0;
+        const long idx = keep ? ((it - a.warm_up_num) / a.thin_rate) % Lrow : 0;
         if (keep && lane == 0) {                                        // samplers.py:436-438
-            a.E_chain[(size_t)m * Lc + idx] = E_initial;
-            a.dE_chain[(size_t)m * Lc + idx] = E_initial - E_previous;
+            a.E_chain[(size_t)m * Lrow + idx] = E_initial;
+            a.dE_chain[(size_t)m * Lrow + idx] = E_initial - E_previous;
         }
         int L; double u;
         if (a.L_tape) { L = a.L_tape[(size_t)m * a.Niter + it - 1]; u = a.u_tape[(size_t)m * a.Niter + it - 1]; }
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128) hmc_random_generic_kernel(hmc_random_args
             for (int i = 0; i < NJ; ++i) q[i] = q_init[i];
         }
         if (keep) {                                                     // samplers.py:465-471 (Q4: negative-index writes skipped)
-            T* dst = q_chain + ((size_t)m * Lc + idx) * D;
+            T* dst = q_chain + ((size_t)m * Lrow + idx) * D;
 #pragma unroll
             for (int i = 0; i < NJ; ++i) { const int j = hmc_dim<NJ>(lane, i); if (j < D) dst[j] = q[i]; }
         }

@@ -111,13 +111,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // so the SECOND part comes out negated; the MMAs that read it set the negate-A bit of the instruction descriptor.
 enum : int { PREC_BF16X3 = 0, PREC_FP16X2 = 1 };
 template <int PREC> struct TcPrec;
-template <> struct TcPrec<PREC_BF16X3> { static constexpr int NPART = 3, NPROD = 6; };
-template <> struct TcPrec<PREC_FP16X2> { static constexpr int NPART = 2, NPROD = 3; };
+template <> struct TcPrec<PREC_BF16X3> { static constexpr int NPART = 3, NPROD = 6; static constexpr bool F16 = false; };
+template <> struct TcPrec<PREC_FP16X2> { static constexpr int NPART = 2, NPROD = 3; static constexpr bool F16 = true; };
 
 template <int PREC>
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& h1, uint32_t& h2, uint32_t& h3) {
     float r0, r1;
-    if constexpr (PREC == PREC_BF16X3) {
+    if constexpr (!TcPrec<PREC>::F16) {
         float s0, s1;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(x1), "f"(x0));
         asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.bf16 %0, lo, %3;\n\tsub.rn.f32.bf16 %1, hi, %4;\n\t}"
@@ -274,6 +274,7 @@ struct TcShared {                       // small per-chain arrays in shared memo
     int gL[TC_M];
     int galive[4][4];                   // per pass number & 3 and group: some slot still has (or wants) a chain
     int stop;                           // set by the issuing warp when the CTA is done (the workers see it after the MMA wait)
+    unsigned int fmax_bits;             // bit pattern of max |F| (set-up only: scale of the fp16 B parts)
 };
 
 constexpr int OUT_SAMPLE = 1 << 29, OUT_STATE = 1 << 30;   // copy the chain's start-point row to q_chain[m][idx] / to state_q[m]
@@ -304,6 +305,26 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     const bool wide = slice == TC_SPL - 1;       // the last slice has 28 dims, the others 24
 
     // ---- one-time set-up ---------------------------------------------------------------------------------------------
+    // fp16 split: the force matrix is scaled by a power of two so that its largest entry sits just below the top of the fp16
+    // range (no part of an entry of interest is an fp16 subnormal, whatever the magnitude of F).  The accumulator then holds
+    // 2^s g; the factor 2^-s is folded into the kick weight and the V sum, exactly.
+    float binv = 1.f, bscale = 1.f;
+    if constexpr (TcPrec<PREC>::F16) {
+        const float* Ft = (const float*)a.target.Ft;
+        const int Dpad = a.target.D_pad;
+        if (tid == 0) sh->fmax_bits = 0u;
+        __syncthreads();
+        unsigned int mx = 0u;
+        for (int t = tid; t < D * D; t += TC_NT) mx = max(mx, __float_as_uint(fabsf(Ft[(size_t)(t / D) * Dpad + (t % D)])));
+        mx = __reduce_max_sync(HMC_FULL_MASK, mx);
+        if (lane == 0) atomicMax(&sh->fmax_bits, mx);
+        __syncthreads();
+        const int e = (int)(sh->fmax_bits >> 23) - 127;         // max |F| in [2^e, 2^(e+1))
+        int sft = (sh->fmax_bits == 0u || e < -100) ? 0 : 14 - e; // scaled maximum in [2^14, 2^15)
+        sft = sft > 100 ? 100 : (sft < -100 ? -100 : sft);
+        bscale = __uint_as_float((unsigned int)(127 + sft) << 23);
+        binv = __uint_as_float((unsigned int)(127 - sft) << 23);
+    }
     {
         const float* Ft = (const float*)a.target.Ft;            // Ft[k][n] = F[n][k]; B row n holds F[n][.] (K-major)
         const int Dpad = a.target.D_pad;
@@ -313,8 +334,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int k0 = kc * 8 + 2 * e, k1 = k0 + 1;
-                const float x0 = (n < D && k0 < D) ? Ft[(size_t)k0 * Dpad + n] : 0.f;
-                const float x1 = (n < D && k1 < D) ? Ft[(size_t)k1 * Dpad + n] : 0.f;
+                const float x0 = (n < D && k0 < D) ? Ft[(size_t)k0 * Dpad + n] * bscale : 0.f;
+                const float x1 = (n < D && k1 < D) ? Ft[(size_t)k1 * Dpad + n] * bscale : 0.f;
                 split_pair<PREC>(x0, x1, w1[e], w2[e], w3[e]);
                 w2[e] ^= 0x80008000u;                           // split_pair returns the second part negated; B holds it as is
             }
@@ -348,10 +369,11 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     const uint32_t tmem_row = tmem + ((uint32_t)(grp * 32) << 16) + (uint32_t)j0;                   // my accumulator slice
     const uint32_t acol = tmem + ((uint32_t)(grp * 32) << 16) + TC_ACOL + 12u * (uint32_t)(slice & 3);  // my A-part columns
     // instruction descriptor: D = f32 (bits 4-5), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16), N >> 3 (17-22), M >> 4 (24-28)
-    constexpr uint32_t fmt = (PREC == PREC_BF16X3) ? 1u : 0u;
+    constexpr uint32_t fmt = TcPrec<PREC>::F16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;      // samplers.py:31
+    const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;         // rows allocated per chain (ring of the last store_ring stored samples)
     float* q_chain = (float*)a.q_chain;
     float* q0g = (float*)a.state_q;
     const float vconst = (float)a.target.v_const;
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + 4 * lane);
                             const float4 v = make_float4(d4.x + mu4.x, d4.y + mu4.y, d4.z + mu4.z, d4.w + mu4.w);
                             if (r & OUT_SAMPLE)
-                                *reinterpret_cast<float4*>(q_chain + (mc * Lc + (size_t)((r & 0xfffffff) - 1)) * D + 4 * lane) = v;
+                                *reinterpret_cast<float4*>(q_chain + (mc * Lrow + (size_t)((r & 0xfffffff) - 1)) * D + 4 * lane) = v;
                             if (r & OUT_STATE) { *reinterpret_cast<float4*>(q0g + mc * D + 4 * lane) = v; state_row = true; }
                         }
                         k = (k == 2) ? 0 : k + 1;
@@ -514,10 +536,10 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                         if (c < nch4) {
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + 4 * c));
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
-                            if (fresh) *reinterpret_cast<float4*>(q_chain + mc * Lc * D + j0 + 4 * c) = v;
+                            if (fresh) *reinterpret_cast<float4*>(q_chain + mc * Lrow * D + j0 + 4 * c) = v;
                             const float4 d4 = make_float4(v.x - mu4.x, v.y - mu4.y, v.z - mu4.z, v.w - mu4.w);
                             *reinterpret_cast<float4*>(q0r + 4 * c) = d4;
-                            if constexpr (PREC == PREC_FP16X2) {       // start point outside the range of the fp16 split: tell the host
+                            if constexpr (TcPrec<PREC>::F16) {       // start point outside the range of the fp16 split: tell the host
                                 if (fresh && !(fmaxf(fmaxf(fabsf(d4.x), fabsf(d4.y)), fmaxf(fabsf(d4.z), fabsf(d4.w))) < 16384.f))
                                     atomicOr(progress + a.Nchain, 1);
                             }
@@ -570,7 +592,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             TP_ADD(0, t0b, t1);
             // point index of the gradient: first = half kick + drift, last = half kick only, interior = second half
             // kick of step l + first half kick of step l+1, drift
-            const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -1.0f : -0.5f);
+            const float kwt = (md == MODE_IDLE) ? 0.f : (md == MODE_MID ? -binv : -0.5f * binv);    // (binv: the accumulator holds g / binv)
             const float dwt = (md == MODE_FIRST || md == MODE_MID) ? 1.f : 0.f;
             const float dt0 = dt_s[0], kdt = kwt * dt0, ddt = dwt * dt0;      // uniform step size (UDT)
             const bool tr = slice == 0 && a.phi_q && m >= 0 && a.chain_id0 + m == 0 && it <= a.N_save_chain0;
@@ -640,7 +662,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
 #pragma unroll
                 for (int s2 = 0; s2 < TC_SPL; ++s2) { const float2 r = sh->red[s2][chain]; sv += r.x; sk += r.y; }
                 const bool tr = a.phi_q && (a.chain_id0 + m) == 0;
-                const float V = fmaf(0.5f, sv, vconst);                         // V(q) = 0.5 d.P d + const (utils.py:213-218)
+                const float V = fmaf(0.5f * binv, sv, vconst);                  // V(q) = 0.5 d.P d + const (utils.py:213-218)
                 if (mdp == MODE_FIRST) {
                     // the draws of this iteration (requested at least two passes ago): samplers.py:431, 441
                     const float Knew = 0.5f * sh->gK[chain];
@@ -649,16 +671,16 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                     // samplers.py:444
                     if (init) {                                                 // samplers.py:416-420
                         const float E0 = V + 0.5f * sh->gK0[chain];
-                        a.E_chain[(size_t)m * Lc] = (double)E0;
-                        a.dE_chain[(size_t)m * Lc] = 0.0;
+                        a.E_chain[(size_t)m * Lrow] = (double)E0;
+                        a.dE_chain[(size_t)m * Lrow] = 0.0;
                         E_prev = E0;
                         init = false;
                     }
                     E_init = V + Knew;                                          // samplers.py:434-438
                     if (it >= a.warm_up_num) {
-                        const long idx = thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate;
-                        a.E_chain[(size_t)m * Lc + idx] = (double)E_init;
-                        a.dE_chain[(size_t)m * Lc + idx] = (double)(E_init - E_prev);
+                        const long idx = ((thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate)) % Lrow;
+                        a.E_chain[(size_t)m * Lrow + idx] = (double)E_init;
+                        a.dE_chain[(size_t)m * Lrow + idx] = (double)(E_init - E_prev);
                     }
                     l = 1;
                     sh->mode[chain] = (l == L) ? MODE_LAST : MODE_MID;
@@ -671,7 +693,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const bool keep = it >= a.warm_up_num;
                     if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
-                    if (keep) oreq = ((thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate) + 1) | OUT_SAMPLE;
+                    if (keep) oreq = ((int)((long)(thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate) % Lrow) + 1) | OUT_SAMPLE;
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
                     if (it >= it_end) {                                         // unit finished: its position goes to state_q
                         a.state_eprev[m] = (double)E_prev;
@@ -861,13 +883,14 @@ int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
     HMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int grid = (a.Nchain + TC_M - 1) / TC_M;
     if (grid > sms) grid = sms;                 // persistent: one CTA per SM, chain slots pull chains from the queue
-    // Sub-blocks: the work queue can hand out (chain, sub-block of the launch's iteration block) units, which makes the
-    // last wave of a launch finer (65,536 chains on 18,944 slots = 3.46 waves).  Measured at that size: 2 sub-blocks
-    // remove 10 % of the passes but the passes of a tail are cheap and every unit costs ~8 passes of set-up and
-    // hand-off, so the launch time is the same (7.00 ms vs 7.04 ms; 3+ sub-blocks are slower).  Off by default;
-    // HMC_B200_TC_SUBBLOCKS=n turns it on (tests/test_random_gpu.py exercises the hand-off).
+    // Sub-blocks: the work queue hands out (chain, sub-block of the launch's iteration block) units, which makes the last wave
+    // of a launch finer: 65,536 chains on 18,944 slots are 3.46 waves, and at the end of a launch the slots run dry one by one
+    // over the length of a unit -- with whole chains as units that tail costs ~half a chain's run time out of 3.5.  A unit costs
+    // ~8 passes of set-up and hand-off (through state_q / state_eprev and a progress word), so units of about 100 iterations
+    // (~1,300 passes) are used when a launch is long enough; short launches (< 200 iterations) keep whole chains (measured at 50
+    // iterations: no gain).  HMC_B200_TC_SUBBLOCKS=n forces n units per chain (tests/test_random_gpu.py exercises the hand-off).
     const int niter = a.iter_end - a.iter_begin;
-    int nsb = 1;
+    int nsb = niter >= 200 ? (niter + 50) / 100 : 1;
     if (const char* e = getenv("HMC_B200_TC_SUBBLOCKS")) { const int n = atoi(e); if (n >= 1 && n <= niter) nsb = n; }
     const int SB = (niter + nsb - 1) / nsb;
     nsb = (niter + SB - 1) / SB;

@@ -12,14 +12,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhmc_b200.so")
 
 HMC_F32, HMC_F64 = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC = 0, 1, 2, 3
-KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST, "tc": KERNEL_TC}
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC, KERNEL_BIGD = 0, 1, 2, 3, 4
+KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "fast": KERNEL_FAST, "tc": KERNEL_TC, "bigd": KERNEL_BIGD}
 FLAG_UNIFORM_DT, FLAG_TC_FP16X2 = 1, 2
 HMC_OK, HMC_E_BADARG, HMC_E_UNSUPPORTED, HMC_E_CUDA, HMC_E_DMAX = 0, 1, 2, 3, 4
 
 EXPORTS = ["hmc_random_run", "hmc_nuts_run", "hmc_diag_moments", "hmc_diag_variogram", "hmc_diag_short_series", "hmc_philox_draws",
            "hmc_ffma_peak", "hmc_version", "hmc_last_error_string", "hmc_start_pts", "hmc_summary_moments", "hmc_summary_hist",
-           "hmc_summary_select"]
+           "hmc_summary_select", "hmc_random_workspace_bytes"]
 
 
 class Target(C.Structure):
@@ -36,7 +36,8 @@ class RandomArgs(C.Structure):
                 ("p_tape", C.c_void_p), ("L_tape", C.c_void_p), ("u_tape", C.c_void_p), ("q_chain", C.c_void_p),
                 ("E_chain", C.c_void_p), ("dE_chain", C.c_void_p), ("state_q", C.c_void_p), ("state_g", C.c_void_p),
                 ("state_eprev", C.c_void_p), ("counters", C.c_void_p), ("phi_q", C.c_void_p), ("phi_len", C.c_void_p),
-                ("decision_chain", C.c_void_p)]
+                ("decision_chain", C.c_void_p), ("store_ring", C.c_int32), ("reserved0", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class NutsArgs(C.Structure):
@@ -65,6 +66,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.hmc_random_run.argtypes = [C.POINTER(RandomArgs), C.c_void_p]
     lib.hmc_random_run.restype = C.c_int
+    lib.hmc_random_workspace_bytes.argtypes = [C.POINTER(RandomArgs)]
+    lib.hmc_random_workspace_bytes.restype = C.c_int64
     lib.hmc_nuts_run.argtypes = [C.POINTER(NutsArgs), C.c_void_p]
     lib.hmc_nuts_run.restype = C.c_int
     lib.hmc_diag_moments.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_void_p,

@@ -11,8 +11,10 @@ Extra keyword-only constructor arguments (defaults keep the reference behaviour)
   own draws as structured tapes, see tests/golden/make_golden.py), on_dmax="assert"|"stop" (NUTS),
   chain_id0=0 / distributed=False (chains sharded over ranks; counters and moments are all-reduced),
   iter_block=None (iterations per kernel launch), target=None (explicit ``MVNSpec`` instead of probing V/dVdq),
-  tc_precision="auto"|"fp16x2"|"bf16x3" (split of the tensor-core gradient product; "auto" = fp16x2, re-run with bf16x3
-  when a start point leaves the fp16 range or the target's scale is far below 1).
+  tc_precision="bf16x3"|"fp16x2" (split of the tensor-core gradient product: three bf16 parts / six tensor passes -- the
+  default of the D = 100 kernel -- or two fp16 parts / three passes -- the default of the large-D GEMM path; at D = 100,
+  rho = 0.95 fp16x2 is 10 % faster at 3x the trajectory error; a D = 100 run whose start points leave the
+  fp16 range repeats itself with bf16x3).
 """
 import os
 
@@ -199,7 +201,7 @@ class HMC_sampler(sampler):
                  cov_p=None, sampler_type="Fixed", L=None, global_dt=True, dt=None,
                  L_low=None, L_high=None, log2L=None, d_max=10, *,
                  dtype="float32", seed=0, kernel="auto", draws=None, on_dmax="assert", chain_id0=0,
-                 distributed=False, iter_block=None, target=None, tc_precision="auto"):
+                 distributed=False, iter_block=None, target=None, tc_precision=None):
         sampler.__init__(self, D=D, target_lnL=None, Nchain=Nchain, Niter=Niter, thin_rate=thin_rate,
                          warm_up_num=warm_up_num)
         self.V = V
@@ -238,7 +240,7 @@ class HMC_sampler(sampler):
         assert dtype in ("float32", "float64")
         assert kernel in _L.KERNELS
         assert on_dmax in ("assert", "stop")
-        assert tc_precision in ("auto", "fp16x2", "bf16x3")
+        assert tc_precision in (None, "fp16x2", "bf16x3")
         self.tc_precision = tc_precision
         self.dtype = dtype
         self.seed = int(seed)
@@ -372,11 +374,16 @@ class HMC_sampler(sampler):
         a.seed = self.seed
         a.target = tgt
         a.flags = _L.FLAG_UNIFORM_DT if np.ndim(self.dt) == 0 or np.all(np.asarray(self.dt) == np.asarray(self.dt).flat[0]) else 0
-        # two-part fp16 split of the tensor-core gradient product unless the target's scale is far below 1 (fp16 subnormals);
-        # start points outside the fp16 range are reported by the kernel (state_g word 16 + Nchain) and the run is repeated with bf16x3
-        small = float(np.min(1.0 / np.sqrt(np.abs(np.diag(self.target.P))))) < 2.0 ** -10
-        if self.tc_precision == "fp16x2" or (self.tc_precision == "auto" and not small):
-            a.flags |= _L.FLAG_TC_FP16X2
+        bigd = self.dtype == "float32" and self._cov_p_identity and D >= 256 and D % 256 == 0 and self.kernel in ("auto", "bigd")
+        if self.tc_precision is None:
+            self.tc_precision = "fp16x2" if bigd else "bf16x3"
+        if self.tc_precision == "fp16x2":
+            # two-part fp16 split of the tensor-core gradient product; needs |q - mu| < 16384 (checked by the kernel, word
+            # 16 + Nchain of state_g) and a target whose scale is not far below 1 (fp16 subnormals)
+            if float(np.min(1.0 / np.sqrt(np.abs(np.diag(self.target.P))))) < 2.0 ** -10:
+                self.tc_precision = "bf16x3"
+            else:
+                a.flags |= _L.FLAG_TC_FP16X2
         a.flags |= (int(os.environ.get("HMC_B200_TILE_VARIANT", "0")) & 0xff) << 8      # tuning knob
         a.q_start = keep["qs"].data_ptr()
         if self.draws is not None:
@@ -390,6 +397,12 @@ class HMC_sampler(sampler):
         a.state_q, a.state_g, a.state_eprev = keep["state_q"].data_ptr(), keep["state_g"].data_ptr(), \
             keep["state_e"].data_ptr()
         a.counters = counters.data_ptr()
+        if bigd:                                  # large-D GEMM path: its scratch (split operands, state, per-chain scalars)
+            nbytes = int(_L.load().hmc_random_workspace_bytes(a))
+            keep["workspace"] = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=dev)
+            base = keep["workspace"].data_ptr()
+            a.workspace = (base + 1023) // 1024 * 1024
+            a.workspace_bytes = nbytes
         if save_chain and owns0:
             keep["phi"] = torch.zeros((N_save_chain0, int(self.L_high), 2), dtype=f64, device=dev)
             keep["phi_len"] = torch.zeros((N_save_chain0,), dtype=torch.int32, device=dev)
@@ -419,8 +432,8 @@ class HMC_sampler(sampler):
         ev1.record()
         ev1.synchronize()
         self.kernel_ms = ev0.elapsed_time(ev1)
-        if (a.flags & _L.FLAG_TC_FP16X2) and self.tc_precision == "auto" and Nc * D >= 64 and \
-                int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0 and self.kernel in ("auto", "tc"):
+        if (a.flags & _L.FLAG_TC_FP16X2) and self.kernel in ("auto", "tc") and \
+                int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0:
             # a start point left the range of the fp16 split (tensor-core kernel only): repeat with the bf16x3 split
             self.tc_precision = "bf16x3"
             return self.gen_sample_random(q_start, N_save_chain0, verbose, quiet)
