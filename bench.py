@@ -288,6 +288,42 @@ def secondary_measurements(torch, dist, S, U, L, lib, rank, world, dev, log):
     except Exception as exc:
         out.append({"name": "nuts_config4", "failed": repr(exc)})
     torch.cuda.empty_cache()
+    # ---- BASELINE config 5: dense-covariance MVN D = 1024, 131,072 chains per GPU (1M over 8), L in [100, 500) ----------------------
+    try:
+        Db, Nb = 1024, int(os.environ.get("HMC_BENCH_BIGD_CHAINS", "131072"))
+        rs = np.random.RandomState(0)
+        lam = np.exp(rs.uniform(np.log(0.05), np.log(100.0), Db))              # log-uniform spectrum, random rotation
+        Qr, _ = np.linalg.qr(rs.standard_normal((Db, Db)))
+        Pb = (Qr / lam) @ Qr.T
+        specb = S.MVNSpec(np.zeros(Db), 0.5 * (Pb + Pb.T), 0.5 * (Db * np.log(2 * np.pi) + np.log(lam).sum()))
+
+        def runbig():
+            q0 = U.start_pts(np.zeros(Db), np.diag(lam.mean() * np.ones(Db)), Nb, device=dev, seed=94, chain_id0=rank * Nb)
+            H = S.HMC_sampler(Db, None, None, Nchain=Nb, Niter=2, warm_up_num=1, sampler_type="Random", dt=DT, L_low=100, L_high=500,
+                              dtype="float32", kernel="auto", seed=8, chain_id0=rank * Nb, target=specb, distributed=(world > 1))
+            H.gen_sample(q0, verbose=False, quiet=True)
+            return H
+        H, t = timed(runbig)
+        ge = H.sum_L + world * Nb * 2
+        alg = ge * 2.0 * Db * Db / (H.kernel_ms * 1e-3) / 1e12
+        try:
+            pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) * world
+        except Exception:
+            pk = 2250.0 * world
+        out.append({"name": "bigd_config5", "what": "dense-covariance MVN D=1024 (log-uniform spectrum on [0.05,100], random rotation), %d chains/GPU, "
+                    "2 iterations, L in [100,500), dt=0.1: one tcgen05 GEMM over all chains per leapfrog step (TMA operands, fp16x2 split, "
+                    "leapfrog fused into the epilogue); all ranks' work over the slowest rank's kernel time" % Nb,
+                    "seconds": t, "kernel_ms": H.kernel_ms, "accept_R": H.accept_R, "tc_precision": H.tc_precision,
+                    "leapfrog_grad_evals_per_sec": H.sum_L / (H.kernel_ms * 1e-3),
+                    "roofline": {"bound": "tensor", "achieved": alg, "peak": pk, "unit": "TFLOP/s", "frac": alg / pk,
+                                 "tensor_tflops_executed": 3.0 * alg, "frac_executed": 3.0 * alg / pk,
+                                 "note": "algorithmic 2 D^2 per gradient evaluation; three fp16 part products executed; the launch ends when the "
+                                         "longest chain ends (sum of two trajectory lengths), so late passes run partly empty tiles"}})
+        del H
+        log("secondary: config 5 done")
+    except Exception as exc:
+        out.append({"name": "bigd_config5", "failed": repr(exc)})
+    torch.cuda.empty_cache()
     # ---- diagnostics kernels on a 6.55 GB float32 stream: algorithmic bytes / kernel time against the measured HBM bandwidth ----
     if rank == 0:
         try:

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 
 RANDOM_FIXTURES = ["random_case1a", "random_d10_thin3", "random_case3c_small", "random_case3d_small",
-                   "random_case2c_small", "random_vecdt_covp"]
-NUTS_FIXTURES = ["nuts_d2", "nuts_d10", "nuts_case3c_small"]
+                   "random_case2c_small", "random_vecdt_covp", "random_constL"]
+NUTS_FIXTURES = ["nuts_d2", "nuts_d10", "nuts_case3c_small", "nuts_covp"]
 
 
 def load(name):

@@ -25,9 +25,14 @@ CASES = [
     ("random_case3d_small", "Random", 100, 0.95, 2, 12, 4, 1, 0.1, dict(L_low=50, L_high=200), 2.0, 3, 0),
     ("random_case2c_small", "Random", 100, 0.0, 4, 40, 10, 1, 0.1, dict(L_low=5, L_high=20), 100.0, 4, 0),
     ("random_vecdt_covp", "Random", 6, 0.5, 4, 50, 10, 2, "vec", dict(L_low=3, L_high=9, cov_p="diag"), 2.0, 5, 0),
+    # the reference's live sampler with L_low = L, L_high = L + 1: randint(7, 8) is always 7 -- a FIXED trajectory length with
+    # the live bookkeeping; pins sampler_type="Fixed" of the B200 build (a silent no-op upstream)
+    ("random_constL", "Random", 10, 0.9, 5, 40, 10, 1, 0.15, dict(L_low=7, L_high=8), 2.0, 9, 6),
     ("nuts_d2", "NUTS", 2, 0.0, 4, 40, 10, 1, 0.3, dict(d_max=10), 2.0, 6, 0),
     ("nuts_d10", "NUTS", 10, 0.95, 3, 30, 10, 2, 0.1, dict(d_max=12), 2.0, 7, 0),
     ("nuts_case3c_small", "NUTS", 100, 0.95, 2, 8, 2, 1, 0.2, dict(d_max=10), 1.0, 8, 0),
+    # NUTS with a non-identity momentum metric (samplers.py:352-356, 811-817, 835-837: force times M^-1, q moved by p, Q9)
+    ("nuts_covp", "NUTS", 6, 0.5, 3, 25, 5, 1, 0.15, dict(d_max=10, cov_p="diag"), 2.0, 10, 0),
 ]
 
 
@@ -72,7 +77,10 @@ def split_tape(tape, sampler, Nchain, Niter, D):
 
 def main():
     ru, rs = ref_shim.load_reference()
+    only = set(sys.argv[1:])
     for (name, sampler, D, rho, Nchain, Niter, warm, thin, dt, extra, sscale, seed, nsave) in CASES:
+        if only and name not in only:
+            continue
         extra = dict(extra)
         q0 = np.zeros(D)
         cov0 = np.diag(np.ones(D)) * (1 - rho)
@@ -119,6 +127,8 @@ def main():
         np.savez_compressed(path, **out)
         print(name, os.path.getsize(path), "bytes; accept", H.accept_R, "Rhat med", np.median(H.R_q))
 
+    if only:
+        return
     # index-helper known answers straight from the reference functions (README:332-358 tables are their print-outs)
     cp = {m: ru.check_points(m).tolist() for m in range(2, 1025, 2)}
     rel = []

@@ -1,0 +1,101 @@
+"""Large-D path (BASELINE config 5: dense-covariance MVN, one tcgen05 GEMM over all chains per leapfrog step, operands by
+TMA, leapfrog update fused into the epilogue; csrc/random_bigd.cu) against the float64 oracle and the generic kernel.
+
+Tolerances: float32 state against the float64 reference: L < 20 on a well-conditioned dense target: rel-L2 1e-5
+(the north star's figure); L in [20,60) at D = 1024 with a log-uniform spectrum on [0.05, 100]: 2e-3, the same bound the
+generic float32 kernel is held to (tests/test_random_gpu.py::test_generic_kernel_large_dimension_matches_oracle)."""
+import numpy as np
+import pytest
+
+from oracle import hmc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_target(D, seed, lam_lo=0.05, lam_hi=100.0):
+    rng = np.random.RandomState(seed)
+    lam = np.exp(rng.uniform(np.log(lam_lo), np.log(lam_hi), D))           # log-uniform spectrum
+    Qm, _ = np.linalg.qr(rng.standard_normal((D, D)))                       # random rotation (role of utils.py:424-441)
+    cov = (Qm * lam) @ Qm.T
+    cov = 0.5 * (cov + cov.T)
+    return O.MVNTarget(rng.standard_normal(D) * 0.5, cov), lam
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16x3"])
+@pytest.mark.parametrize("D,B,Llo,Lhi,tol", [(256, 300, 5, 20, 1e-5), (1024, 200, 20, 60, 2e-3)])
+def test_bigd_teacher_forced_against_oracle(D, B, Llo, Lhi, tol, prec):
+    import samplers as S
+    tgt, lam = _dense_target(D, 7, 0.5 if D == 256 else 0.05, 20.0 if D == 256 else 100.0)
+    rng = np.random.RandomState(11)
+    q_init = (tgt.q0 + rng.standard_normal((B, D)) @ np.linalg.cholesky(tgt.cov0).T).astype(np.float32).astype(float)
+    p = rng.standard_normal((B, D)).astype(np.float32).astype(float)
+    L = rng.randint(Llo, Lhi, size=B).astype(np.int32)
+    u = rng.random_sample(B)
+    want = O.one_iteration_batch(tgt, q_init, p, L, u, 0.1)
+    p_tape = np.zeros((B, 2, D))
+    p_tape[:, 1] = p
+    H = S.HMC_sampler(D, None, None, Nchain=B, Niter=1, sampler_type="Random", dt=0.1, L_low=Llo, L_high=Lhi, dtype="float32",
+                      kernel="bigd", tc_precision=prec, target=S.MVNSpec(tgt.q0, tgt.inv_cov0, tgt.const),
+                      draws=dict(p_tape=p_tape, L_tape=L.reshape(B, 1), u_tape=u.reshape(B, 1)))
+    H.gen_sample(q_init, verbose=False, quiet=True)
+    got = H.q_chain[:, 1, :]
+    np.testing.assert_array_equal(H.q_chain[:, 0, :], q_init)
+    moved = np.linalg.norm(got - q_init, axis=1) > 1e-6 * np.linalg.norm(q_init - tgt.q0, axis=1)
+    E_scale = np.maximum(1.0, np.abs(want["E_init"]))
+    near_tie = (want["dE"] >= 0) & (np.abs(np.log(u) + want["dE"]) < 1e-4 * E_scale)
+    differ = moved != (want["decision"] == 1)
+    assert not np.any(differ & ~near_tie), "%d decision flips away from ties" % int(np.sum(differ & ~near_tie))
+    acc = moved & ~differ
+    assert acc.sum() > 0.5 * B
+    amp = np.maximum(np.linalg.norm(want["q_prop"] - tgt.q0, axis=1), np.linalg.norm(q_init - tgt.q0, axis=1))
+    rel = np.linalg.norm(got[acc] - want["q_prop"][acc], axis=1) / amp[acc]
+    assert rel.max() < tol, "worst rel-L2 trajectory error %.3g" % rel.max()
+    np.testing.assert_allclose(H.E_chain[:, 1, 0], want["E_init"], rtol=1e-4, atol=1e-2)
+    assert H.sum_L == int(L.sum())
+    assert H.N_total_steps == B * 3 + D * int((L.astype(np.int64) ** 2).sum())
+
+
+def test_bigd_free_running_matches_generic_kernel():
+    """Philox draws, several iterations with warm-up and thinning, iteration blocks (resume through state_q), chain-0 trace:
+    same draws as the generic float32 kernel => same trajectory lengths, same first stored samples, matching acceptance."""
+    import samplers as S
+    D, Nchain, Niter = 256, 500, 13
+    tgt, _ = _dense_target(D, 3, 0.5, 20.0)
+    spec = S.MVNSpec(tgt.q0, tgt.inv_cov0, tgt.const)
+    q_start = (tgt.q0 + np.random.RandomState(5).standard_normal((Nchain, D)) * 1.5).astype(np.float32)
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=2, warm_up_num=3, sampler_type="Random", dt=0.12, L_low=4, L_high=11,
+              dtype="float32", seed=21, target=spec, chain_id0=1000)
+    F = S.HMC_sampler(D, None, None, kernel="bigd", iter_block=4, **kw)
+    F.gen_sample(q_start, verbose=False, quiet=True)
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L and F.N_total_steps == G.N_total_steps
+    assert F.q_chain.shape == G.q_chain.shape == (Nchain, 1 + (Niter - 3) // 2, D)
+    amp = np.linalg.norm(q_start.astype(float) - tgt.q0, axis=1)
+    rel0 = np.linalg.norm(F.q_chain[:, 0] - G.q_chain[:, 0], axis=1) / amp
+    assert np.quantile(rel0, 0.98) < 1e-4
+    rel_last = np.linalg.norm(F.q_chain[:, -1] - G.q_chain[:, -1], axis=1) / amp
+    assert np.mean(rel_last < 1e-3) > 0.9
+    assert abs(F.accept_R - G.accept_R) < 2e-2 and abs(F.accept_R_warm_up - G.accept_R_warm_up) < 2e-2
+    same = rel_last < 1e-3
+    np.testing.assert_allclose(F.E_chain[same, :, 0], G.E_chain[same, :, 0], rtol=2e-4, atol=2e-3)
+    F.compute_convergence_stats()
+    assert np.all(np.isfinite(F.R_q)) and np.all(F.n_eff_q > 0)
+
+
+def test_bigd_chain0_trace_and_auto_dispatch():
+    import samplers as S
+    D, Nchain, Niter = 256, 130, 5
+    tgt, _ = _dense_target(D, 9, 0.5, 20.0)
+    spec = S.MVNSpec(tgt.q0, tgt.inv_cov0, tgt.const)
+    q_start = (tgt.q0 + np.random.RandomState(6).standard_normal((Nchain, D))).astype(np.float32)
+    kw = dict(Nchain=Nchain, Niter=Niter, sampler_type="Random", dt=0.1, L_low=3, L_high=8, dtype="float32", seed=2, target=spec)
+    F = S.HMC_sampler(D, None, None, kernel="auto", **kw)                    # D % 256 == 0: the large-D path
+    F.gen_sample(q_start, N_save_chain0=4, verbose=False, quiet=True)
+    assert F.tc_precision == "fp16x2"
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, N_save_chain0=4, verbose=False, quiet=True)
+    assert [len(x) for x in F.phi_q] == [len(x) for x in G.phi_q]
+    np.testing.assert_allclose(np.concatenate(F.phi_q), np.concatenate(G.phi_q), rtol=0, atol=2e-4)
+    np.testing.assert_array_equal(F.decision_chain, G.decision_chain)
+    assert F.sum_L == G.sum_L

@@ -48,7 +48,7 @@ def test_nuts_matches_reference(name):
     D, Nchain, Niter = int(fx["D"]), int(fx["Nchain"]), int(fx["Niter"])
     draws = ChainTapeDraws(fx["p_tape"], fx["dir_tape"], fx["u_tape"])
     R = O.gen_sample_NUTS(D, tgt.V, tgt.dVdq, fx["q_start"], draws, Nchain, Niter, int(fx["thin_rate"]),
-                          int(fx["warm_up_num"]), float(fx["dt"]), int(fx["d_max"]), record=True)
+                          int(fx["warm_up_num"]), float(fx["dt"]), int(fx["d_max"]), cov_p=fx["cov_p"], record=True)
     scale = max(1.0, np.abs(fx["E_chain"]).max())
     np.testing.assert_allclose(R.q_chain, fx["q_chain"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(R.E_chain, fx["E_chain"], rtol=0, atol=1e-12 * scale)

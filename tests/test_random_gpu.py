@@ -182,16 +182,32 @@ def test_sharding_invariance_and_iteration_blocks():
     np.testing.assert_array_equal(np.concatenate([a.dE_chain, b.dE_chain]), full.dE_chain)
 
 
-def test_fixed_sampler_is_random_with_constant_L():
+def test_fixed_sampler_matches_reference_constant_length_run():
+    """sampler_type="Fixed" (a silent no-op upstream, samplers.py:378-383) runs the live random-length loop with a constant
+    L.  Pinned to the REAL reference: the fixture random_constL is the reference's Random sampler with L_low = L, L_high =
+    L + 1 (np.random.randint(7, 8) is always 7; tests/golden/make_golden.py) -- same draws, float64 kernel, free running:
+    the whole sample stream, energies, acceptance, N_total_steps and the chain-0 record must be the reference's."""
     import samplers as S
-    D, Nchain, Niter = 4, 8, 20
-    tgt = O.MVNTarget(np.zeros(D), np.eye(D))
-    q_start = np.random.RandomState(1).standard_normal((Nchain, D))
-    H = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=Nchain, Niter=Niter, sampler_type="Fixed", L=7, dt=0.1,
-                      dtype="float64", kernel="generic", seed=5)
-    H.gen_sample(q_start, verbose=False)
-    assert H.sum_L == 7 * Nchain * Niter
-    assert H.N_total_steps == Nchain * (1 + 2 * Niter) + D * 49 * Nchain * Niter
+    fx = load("random_constL")
+    D, Lfix = int(fx["D"]), int(fx["L_low"])
+    assert np.all(fx["L_tape"] == Lfix)
+    nsave = int(fx["N_save_chain0"])
+    H = S.HMC_sampler(D, None, None, Nchain=int(fx["Nchain"]), Niter=int(fx["Niter"]), thin_rate=int(fx["thin_rate"]),
+                      warm_up_num=int(fx["warm_up_num"]), sampler_type="Fixed", L=Lfix, dt=float(fx["dt"]), dtype="float64",
+                      kernel="generic", target=S.MVNSpec.from_cov(fx["q0"], fx["cov0"]),
+                      draws=dict(p_tape=fx["p_tape"], L_tape=fx["L_tape"], u_tape=fx["u_tape"]))
+    H.gen_sample(fx["q_start"], N_save_chain0=nsave, verbose=False)
+    np.testing.assert_allclose(H.q_chain, fx["q_chain"], rtol=0, atol=1e-9 * max(1.0, np.abs(fx["q_chain"]).max()))
+    np.testing.assert_allclose(H.E_chain, fx["E_chain"], rtol=0, atol=1e-9 * max(1.0, np.abs(fx["E_chain"]).max()))
+    assert H.accept_R == pytest.approx(float(fx["accept_R"]), abs=1e-15)
+    assert H.N_total_steps == int(fx["N_total_steps"])
+    np.testing.assert_array_equal(H.decision_chain, fx["decision_chain"])
+    # and with the kernels' own Philox draws: every trajectory has exactly L steps
+    P = S.HMC_sampler(4, None, None, Nchain=8, Niter=20, sampler_type="Fixed", L=7, dt=0.1, dtype="float64", kernel="generic",
+                      seed=5, target=S.MVNSpec.from_cov(np.zeros(4), np.eye(4)))
+    P.gen_sample(np.random.RandomState(1).standard_normal((8, 4)), verbose=False)
+    assert P.sum_L == 7 * 8 * 20
+    assert P.N_total_steps == 8 * (1 + 2 * 20) + 4 * 49 * 8 * 20
 
 
 def test_target_extraction_and_errors():

@@ -22,6 +22,8 @@ int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream);
 bool hmc_random_bigd_supported(const hmc_random_args& a, const char** why);
 size_t hmc_random_bigd_workspace(const hmc_random_args& a);
 int hmc_nuts_run_generic(const hmc_nuts_args& a, cudaStream_t stream);
+int hmc_nuts_run_tc(const hmc_nuts_args& a, cudaStream_t stream);
+bool hmc_nuts_tc_supported(const hmc_nuts_args& a, const char** why);
 
 extern "C" int hmc_version(void) { return HMC_B200_VERSION; }
 extern "C" const char* hmc_last_error_string(void) { return g_err; }
@@ -92,8 +94,11 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
 
 extern "C" int64_t hmc_random_workspace_bytes(const hmc_random_args* args) {
     const char* why = "";
-    if (!args || !hmc_random_bigd_supported(*args, &why)) return 0;
-    return (int64_t)hmc_random_bigd_workspace(*args);
+    if (!args) return 0;
+    hmc_random_args a = *args;                      // (the iteration range of the launch does not matter for the size)
+    a.iter_begin = 0; a.iter_end = 1;
+    if (!hmc_random_bigd_supported(a, &why)) return 0;
+    return (int64_t)hmc_random_bigd_workspace(a);
 }
 
 extern "C" int hmc_nuts_run(const hmc_nuts_args* args, void* cuda_stream) {
@@ -111,8 +116,22 @@ extern "C" int hmc_nuts_run(const hmc_nuts_args* args, void* cuda_stream) {
     HMC_REQUIRE(a.iter_begin > 0 || a.q_start, "q_start required when iter_begin == 0");
     HMC_REQUIRE((a.p_tape == nullptr) == (a.dir_tape == nullptr) && (a.dir_tape == nullptr) == (a.u_tape == nullptr),
                 "p_tape, dir_tape and u_tape must be given together");
-    HMC_REQUIRE(a.target.Mit == nullptr && a.target.Pt == nullptr,
-                "NUTS kernel covers the identity momentum metric only");
+    HMC_REQUIRE((a.target.Mit == nullptr) == (a.target.Pt == nullptr) && (a.target.Pt == nullptr) == (a.target.Lct == nullptr),
+                "dense momentum metric: target.Pt, Mit and Lct must be given together");
+    const char* why = "";
+    int kernel = a.kernel;
+    if (kernel == HMC_KERNEL_AUTO) kernel = hmc_nuts_tc_supported(a, &why) ? HMC_KERNEL_TC : HMC_KERNEL_GENERIC;
+    if (kernel == HMC_KERNEL_TC) {
+        if (!hmc_nuts_tc_supported(a, &why)) {
+            hmc_set_error("tensor-core NUTS kernel does not cover this configuration: %s", why);
+            return HMC_E_UNSUPPORTED;
+        }
+        return hmc_nuts_run_tc(a, (cudaStream_t)cuda_stream);
+    }
+    if (kernel != HMC_KERNEL_GENERIC) {
+        hmc_set_error("NUTS: kernel must be auto, generic or tc");
+        return HMC_E_BADARG;
+    }
     return hmc_nuts_run_generic(a, (cudaStream_t)cuda_stream);
 }
 

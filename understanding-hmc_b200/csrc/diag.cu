@@ -366,6 +366,119 @@ __global__ void __launch_bounds__(256, 2) diag_variogram_f32x2_kernel(const floa
     for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
 }
 
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32); }
+
+// Windowed variogram in CROSS-PRODUCT form: with y = x - x[0] (the chain's first sample: the sums are shift invariant),
+//   sum_{i >= t} (y_i - y_{i-t})^2 = sum_{i >= t} y_i^2 + sum_{i < n-t} y_i^2 - 2 sum_{i >= t} y_i y_{i-t},
+// so a (sample, lag) pair costs ONE fused multiply-add instead of a subtraction and a multiply-add: the float32 pipe drops
+// below the HBM time of a pass.  The two sums of squares of lag t = lag0 + k are those of lag0 (accumulated along the two
+// streams the kernel reads anyway) minus the first / last k terms, which are folded into the lag's accumulator (half each)
+// from 2 (NL - 1) re-read samples per chain.  The float32 cancellation costs ~1e-6 / (1 - rho_t) relative accuracy of V_t,
+// i.e. ~1e-6 absolute in rho_t (HMC_B200_DIAG_DIFF=1 selects the difference form above, e.g. for chains that drift far
+// within the window).  Same window / unrolling scheme as diag_variogram_f32x2_kernel.
+template <int NL>
+__global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
+                                                                    long stride_chain, int d0, int Dt, int spb, int lag0, int nlags,
+                                                                    double* __restrict__ out) {
+    extern __shared__ double sm[];   // [NL][Dt]
+    for (int t = threadIdx.x; t < NL * Dt; t += blockDim.x) sm[t] = 0.0;
+    __syncthreads();
+    const int D2 = Dt >> 1;
+    const int dp = threadIdx.x % D2, sl = threadIdx.x / D2;
+    constexpr int H = NL / 2;
+    if (sl < spb) {
+        const long nseries = 2 * Nchain;
+        const long p2 = pitch >> 1;
+        for (long s = (long)blockIdx.x * spb + sl; s < nseries; s += (long)gridDim.x * spb) {
+            const f32x2* x = reinterpret_cast<const f32x2*>(q + (s >> 1) * stride_chain + (s & 1) * n * pitch + d0) + dp;
+            const f32x2 c = x[0];
+            f32x2 w[NL], acc[NL];       // acc[k] = sum y_i y_{i - lag0 - k}  (+ half the excluded squares, folded in below)
+            f32x2 sa = 0ull, sb = 0ull;  // sum of squares of the two streams: y_i (i >= lag0) and y_j (j < n - lag0)
+#pragma unroll
+            for (int k = 0; k < NL; ++k) { w[k] = 0ull; acc[k] = 0ull; }
+            const long nsteps = n - lag0;
+            long j0 = 0;
+            if (nsteps > 0) {
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    f32x2 xa[H], wn[H];
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const long j = hb * H + r;
+                        xa[r] = (j < nsteps) ? sub2(x[(lag0 + j) * p2], c) : 0ull;
+                        wn[r] = (j < nsteps) ? sub2(x[j * p2], c) : 0ull;
+                    }
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const int rr = hb * H + r;
+                        if (rr < nsteps) {
+                            w[rr] = wn[r];
+                            sa = fma2(xa[r], xa[r], sa); sb = fma2(wn[r], wn[r], sb);
+#pragma unroll
+                            for (int k = 0; k < NL; ++k)
+                                if (k <= rr) acc[k] = fma2(xa[r], w[(rr - k + NL) % NL], acc[k]);
+                        }
+                    }
+                }
+                j0 = NL;
+            }
+            for (; j0 + NL <= nsteps; j0 += NL) {
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    f32x2 xa[H], wn[H];
+#pragma unroll
+                    for (int r = 0; r < H; ++r) { xa[r] = sub2(x[(lag0 + j0 + hb * H + r) * p2], c); wn[r] = sub2(x[(j0 + hb * H + r) * p2], c); }
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        const int rr = hb * H + r;
+                        w[rr] = wn[r];
+                        sa = fma2(xa[r], xa[r], sa); sb = fma2(wn[r], wn[r], sb);
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) acc[k] = fma2(xa[r], w[(rr - k + NL) % NL], acc[k]);
+                    }
+                }
+            }
+            if (j0 < nsteps) {
+#pragma unroll
+                for (int rr = 0; rr < NL; ++rr) {
+                    const long j = j0 + rr;
+                    if (j < nsteps) {
+                        const f32x2 xa = sub2(x[(lag0 + j) * p2], c);
+                        w[rr] = sub2(x[j * p2], c);
+                        sa = fma2(xa, xa, sa); sb = fma2(w[rr], w[rr], sb);
+#pragma unroll
+                        for (int k = 0; k < NL; ++k) acc[k] = fma2(xa, w[(rr - k + NL) % NL], acc[k]);
+                    }
+                }
+            }
+            // lag lag0 + k leaves out the first k samples of the upper stream and the last k of the lower one
+            if (nsteps > 0) {
+                f32x2 pre = 0ull, suf = 0ull;
+                const f32x2 half2 = pack2(0.5f, 0.5f);
+#pragma unroll
+                for (int t = 0; t < NL - 1; ++t) {
+                    if (t < nsteps) {
+                        const f32x2 a1 = sub2(x[(lag0 + t) * p2], c), b1 = sub2(x[(nsteps - 1 - t) * p2], c);
+                        pre = fma2(a1, a1, pre); suf = fma2(b1, b1, suf);
+                        acc[t + 1] = fma2(half2, pre, acc[t + 1]);
+                        acc[t + 1] = fma2(half2, suf, acc[t + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NL; ++k) {
+                if (k < nlags && k < nsteps) {       // sum (y_i - y_{i-t})^2 = sa + sb - 2 (cross + half the excluded squares)
+                    atomicAdd(&sm[k * Dt + 2 * dp], ((double)lo_of(sa) + (double)lo_of(sb)) - 2.0 * (double)lo_of(acc[k]));
+                    atomicAdd(&sm[k * Dt + 2 * dp + 1], ((double)hi_of(sa) + (double)hi_of(sb)) - 2.0 * (double)hi_of(acc[k]));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nlags * Dt; t += blockDim.x) atomicAdd(out + (t / Dt) * D + d0 + (t % Dt), sm[t]);
+}
+
 int grid_for(long nseries, int spb, int per_sm = 8) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -468,8 +581,13 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
                 const int Dt = (D - d0 < 512) ? D - d0 : 512;
                 const int spb = 256 / (Dt / 2);
                 const size_t smem = sizeof(double) * NLP * Dt;
-                HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_f32x2_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                diag_variogram_f32x2_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
+                if (getenv("HMC_B200_DIAG_DIFF")) {
+                    HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_f32x2_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    diag_variogram_f32x2_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
+                } else {
+                    HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_cross_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    diag_variogram_cross_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
+                }
             }
         }
         HMC_CUDA_CHECK(cudaGetLastError());

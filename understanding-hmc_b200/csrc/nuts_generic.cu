@@ -1,6 +1,7 @@
 // NUTS kernel: ONE WARP PER CHAIN runs the reference's iterative tree doubling
 // (HMC_sampler.gen_sample_NUTS, /root/reference/samplers.py:495-808) as a per-chain state machine; float or
-// double; identity momentum metric.  Lane l owns dimensions l, l+32, ...; control flow is warp-uniform (every
+// double; identity or dense momentum metric (cov_p != I: the force is M^-1 P (q - mu) as the reference writes it, Q9,
+// V and K take their own mat-vecs with P and M^-1, momenta are Lc z; samplers.py:352-356, 811-817, 825-829, 835-837).  Lane l owns dimensions l, l+32, ...; control flow is warp-uniform (every
 // per-chain scalar is computed redundantly by all lanes, in float64 -- SURVEY H5: the progressive-sampling
 // weights exp(E_max - E) overflow float32).
 //
@@ -26,6 +27,9 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = a.target.D, Dp = a.target.D_pad;
     const T* Ft = (const T*)a.target.Ft;
+    const T* Pt = (const T*)a.target.Pt;        // NULL for the identity metric (then F == P)
+    const T* Mit = (const T*)a.target.Mit;
+    const T* Lct = (const T*)a.target.Lct;
     T* xs = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * Dp;
     {
         T* s = (T*)smem_raw + (size_t)(blockDim.x >> 5) * Dp;
@@ -79,17 +83,29 @@ __global__ void __launch_bounds__(128) hmc_nuts_generic_kernel(hmc_nuts_args a) 
                     p[i] = (T)(r == 0 ? z.x : r == 1 ? z.y : r == 2 ? z.z : z.w);
                 } else p[i] = T(0);
             }
+            if (Lct) {                        // p = Lc z ~ N(0, cov_p)   (samplers.py:829)
+#pragma unroll
+                for (int i = 0; i < NJ; ++i) t1[i] = p[i];
+                matvec_t<T, NJ, false>(Lct, D, Dp, t1, p, lane, xs);
+            }
         }
     };
-    auto force = [&]() {                      // f = P (q - mu)
+    auto force = [&]() {                      // f = M^-1 P (q - mu)
 #pragma unroll
         for (int i = 0; i < NJ; ++i) d[i] = q[i] - mu[i];
         matvec_t<T, NJ, SM>(Ft, D, Dp, d, f, lane, xs);
     };
     auto energy = [&]() -> double {           // E(q, p) with d, f current (samplers.py:819-823): one warp reduction
         T s = T(0);
+        if (Pt) {                             // dense metric: V = 0.5 d.P d, K = 0.5 p.M^-1 p (samplers.py:811-817)
+            matvec_t<T, NJ, false>(Pt, D, Dp, d, t1, lane, xs);
+            matvec_t<T, NJ, false>(Mit, D, Dp, p, t2, lane, xs);
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) s = fma(d[i], f[i], fma(p[i], p[i], s));
+            for (int i = 0; i < NJ; ++i) s = fma(d[i], t1[i], fma(p[i], t2[i], s));
+        } else {
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) s = fma(d[i], f[i], fma(p[i], p[i], s));
+        }
         return 0.5 * (double)warp_sum<T>(s) + vconst;
     };
     auto leap = [&]() {                       // one leapfrog step, f = force at q on entry and on exit (samplers.py:831-839)

@@ -8,7 +8,7 @@
 //   bigd_gemm_step   persistent CTAs over (128 chains x 256 dimensions) tiles, K = D.  Warp 0 issues the TMA loads
 //                    (cp.async.bulk.tensor, 128-byte swizzle, 2 stages of K = 64), warp 1 issues the tcgen05.mma
 //                    (cta_group::1, kind::f16, M = 128, N = 256, fp32 accumulators double-buffered in the 512 TMEM columns),
-//                    warps 2..5 are the epilogue: tcgen05.ld of the tile, per-chain kick / drift weights by trajectory
+//                    warps 2..9 are the epilogue: tcgen05.ld of the tile, per-chain kick / drift weights by trajectory
 //                    phase (first point: half kick + drift, interior: full kick + drift, last: half kick), momentum and
 //                    position updated in place, the NEXT pass's A operand (the split position) written, partial sums of
 //                    q.g and p.p per (chain, column tile) for the energies.
@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -36,18 +37,22 @@ constexpr int BM = 128;            // chains per tile (UMMA M)
 constexpr int BN_MAX = 256;        // dimensions per tile (UMMA N; fp32 accumulator columns): 256 for the two-part split, 128 for the three-part one (shared memory)
 constexpr int BK = 64;             // K per stage: 64 16-bit elements = one 128-byte swizzle row
 constexpr int STAGES = 2;
-constexpr int EB = 16;             // epilogue column block
-constexpr int NTHREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int EB = 8;              // epilogue column block
+constexpr int NEPI = 8;            // epilogue warps: two per TMEM lane quarter, alternating column blocks
+constexpr int NTHREADS = 64 + 32 * NEPI;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 enum : int { MD_IDLE = 0, MD_FIRST = 1, MD_MID = 2, MD_LAST = 3, MD_PENDING = 4 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+// (a wait that lasts longer than ~4 s of SM clocks means a lost TMA / MMA completion: abort the kernel instead of hanging the GPU)
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     uint32_t done = 0;
+    const long long t0 = clock64();
     while (!done) {
         asm volatile("{\n\t.reg .pred pw;\n\tmbarrier.try_wait.parity.shared::cta.b64 pw, [%1], %2;\n\tselp.u32 %0, 1, 0, pw;\n\t}"
                      : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 8000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
@@ -107,7 +112,7 @@ struct BigdWs {                      // workspace carved by the host (all device
     float* x;                        // [Ncp][D] shifted position q - mu
     float* x0;                       // [Ncp][D] position at the start of the running trajectory
     float* p;                        // [Ncp][D] momentum
-    float* red;                      // [Ncp][NT][2] partial (q.g, p.p) per column tile of the last pass
+    float* red;                      // [Ncp][NT][2][2] partial (q.g, p.p) per column tile and epilogue warp of the last pass
     int* mode;                       // [Ncp] MD_*
     int* l;                          // [Ncp] leapfrog steps done in the running trajectory
     int* L;                          // [Ncp] its length
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
     unsigned char* stage_base = smem;
     unsigned char* epi = smem + STAGES * STAGE_BYTES;                           // epilogue staging, per warp
     constexpr int EPI_WARP_BYTES = 2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 4 * EPI_WARP_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi + NEPI * EPI_WARP_BYTES);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + STAGES;       // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;   // [2]
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 1) {
@@ -217,12 +222,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 = chains of the tile =====
-        const int quarter = warp & 3;
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 = chains of the tile; the two warps of a lane quarter take
+        //       alternating 8-column blocks.  Rows travel through a padded shared-memory tile so that global accesses are row
+        //       segments (coalesced) while the arithmetic is one thread per chain (the layout tcgen05.ld delivers). =========
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         float* Ps = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);     // [32][EB + 1]
         float* Xs = Ps + 32 * (EB + 1) + 16;                                        // [32][EB + 1] (16 words on: other banks than Ps)
         uint32_t* Hs = reinterpret_cast<uint32_t*>(Xs + 32 * (EB + 1));            // [NPART][32][EB / 2 + 1]
         uint32_t nt_done = 0;
+        const int sub = lane >> 3, col = lane & 7;              // global <-> shared: 8 lanes per row segment, 4 row segments per instruction
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int mt = t / NT, nt = t % NT;
             if (!w.tile_active[mt]) continue;
@@ -237,18 +245,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;");
             float hv = 0.f, hk = 0.f;
             if (live) {
-                for (int cb = 0; cb < BN / EB; ++cb) {
+                for (int cb = half; cb < BN / EB; cb += 2) {
                     const int c0 = nt * BN + cb * EB;
-                    // coalesced rows -> shared (lanes 0..15: momentum, lanes 16..31: position)
+                    // row segments -> shared: lanes (sub 0, 2): momentum of rows i, i + 1; (sub 1, 3): position; all 16 loads in flight
                     {
-                        const float* src = (lane < 16 ? w.p : w.x) + c0 + (lane & 15);
-                        float* dst = (lane < 16 ? Ps : Xs) + (lane & 15);
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) dst[i * (EB + 1)] = src[(size_t)(row0 + i) * D];
+                        const float* src = ((sub & 1) ? w.x : w.p) + c0 + col + (size_t)(row0 + (sub >> 1)) * D;
+                        float* dst = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + (size_t)(2 * i) * D);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[2 * i * (EB + 1)] = v[i];
                     }
                     __syncwarp();
-                    uint32_t gv[16];
-                    tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cb * EB), gv);
+                    uint32_t gv[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7])
+                                 : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cb * EB)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     float xn[EB];
 #pragma unroll
                     for (int j = 0; j < EB; ++j) {
@@ -270,27 +284,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                         for (int pt = 0; pt < NPART; ++pt) Hs[(pt * 32 + lane) * (EB / 2 + 1) + j] = h[pt];
                     }
                     __syncwarp();
-                    // shared -> coalesced rows
+                    // shared -> row segments
                     {
-                        float* dst = (lane < 16 ? w.p : w.x) + c0 + (lane & 15);
-                        const float* src = (lane < 16 ? Ps : Xs) + (lane & 15);
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) dst[(size_t)(row0 + i) * D] = src[i * (EB + 1)];
+                        float* dst = ((sub & 1) ? w.x : w.p) + c0 + col + (size_t)(row0 + (sub >> 1)) * D;
+                        const float* src = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) __stcs(dst + (size_t)(2 * i) * D, src[2 * i * (EB + 1)]);
                     }
 #pragma unroll
                     for (int pt = 0; pt < NPART; ++pt) {
-                        // 8 words per row and part: lanes 8 r .. 8 r + 7 store row i + r (four rows per instruction)
-                        uint32_t* dstp = reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp) * D) + (c0 >> 1) + (lane & 7);
-#pragma unroll 4
-                        for (int i = 0; i < 32; i += 4) {
-                            const int r = i + (lane >> 3);
-                            dstp[(size_t)(row0 + r) * (D >> 1)] = Hs[(pt * 32 + r) * (EB / 2 + 1) + (lane & 7)];
+                        // 4 words per row and part: lanes 4 r .. 4 r + 3 store row i + r (eight rows per instruction)
+                        uint32_t* dstp = reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp) * D) + (c0 >> 1) + (lane & 3);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const int r = i + (lane >> 2);
+                            dstp[(size_t)(row0 + r) * (D >> 1)] = Hs[(pt * 32 + r) * (EB / 2 + 1) + (lane & 3)];
                         }
                     }
                     __syncwarp();
                 }
             }
-            if (chain < Nchain) { w.red[((size_t)chain * NT + nt) * 2] = hv; w.red[((size_t)chain * NT + nt) * 2 + 1] = hk; }
+            if (chain < Nchain) {
+                float* rd = w.red + (((size_t)chain * NT + nt) * 2 + half) * 2;
+                rd[0] = hv; rd[1] = hk;
+            }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + as);
@@ -387,7 +404,7 @@ __global__ void __launch_bounds__(BM) bigd_events(hmc_random_args a, BigdWs w, i
     unsigned long long acc_warm = 0, acc_post = 0, sL = 0, sL2 = 0;
     if (md == MD_FIRST || md == MD_MID || md == MD_LAST) {
         float hv = 0.f, hk = 0.f;
-        for (int t = 0; t < w.NT; ++t) { hv += w.red[((size_t)m * w.NT + t) * 2]; hk += w.red[((size_t)m * w.NT + t) * 2 + 1]; }
+        for (int t = 0; t < 2 * w.NT; ++t) { hv += w.red[((size_t)m * 2 * w.NT + t) * 2]; hk += w.red[((size_t)m * 2 * w.NT + t) * 2 + 1]; }
         const float V = fmaf(0.5f * w.binv, hv, (float)a.target.v_const);           // V(q) at the point the gradient was taken
         const int it = w.it[m];
         const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
@@ -567,7 +584,7 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
     w.x = (float*)take((size_t)Ncp * D * 4);
     w.x0 = (float*)take((size_t)Ncp * D * 4);
     w.p = (float*)take((size_t)Ncp * D * 4);
-    w.red = (float*)take((size_t)Ncp * NT * 2 * 4);
+    w.red = (float*)take((size_t)Ncp * NT * 2 * 2 * 4);
     w.mode = (int*)take(Ncp * 4); w.l = (int*)take(Ncp * 4); w.L = (int*)take(Ncp * 4); w.it = (int*)take(Ncp * 4); w.init = (int*)take(Ncp * 4);
     w.K_new = (float*)take(Ncp * 4); w.K0 = (float*)take(Ncp * 4); w.lnu = (float*)take(Ncp * 4); w.E_init = (float*)take(Ncp * 4);
     w.E_prev = (float*)take(Ncp * 4);
@@ -579,7 +596,7 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
 
 template <int NPART, int BN>
 constexpr size_t gemm_smem_bytes() {
-    return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + 4 * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 16 * 8 + 64;
+    return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + NEPI * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 16 * 8 + 64;
 }
 static_assert(gemm_smem_bytes<2, 256>() <= 232448 && gemm_smem_bytes<3, 128>() <= 232448, "shared memory of the large-D GEMM exceeds 227 KB");
 
@@ -625,7 +642,27 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     HMC_CUDA_CHECK(cudaMallocHost(&running_h, 4));
     const long max_pass = (long)(a.iter_end - a.iter_begin) * (a.L_high + 1) + 8;
     int rc = HMC_OK;
+    // HMC_B200_BIGD_TIMING=1: CUDA-event times of the three kernels of passes 4..11 on stderr (measurement aid)
+    const bool timing = getenv("HMC_B200_BIGD_TIMING") != nullptr;
+    cudaEvent_t ev[4];
+    float tsum[3] = {0.f, 0.f, 0.f};
+    if (timing) for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
     for (long pass = 0; pass < max_pass; ++pass) {
+        if (timing && pass >= 4 && pass < 12) {
+            cudaEventRecord(ev[0], stream);
+            bigd_gemm_step<NPART, BN><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, w, a.Nchain, D, (const float*)a.target.dt);
+            cudaEventRecord(ev[1], stream);
+            cudaMemsetAsync(w.counters + 2, 0, 4, stream);
+            bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
+            cudaEventRecord(ev[2], stream);
+            bigd_trajectory_end<NPART><<<sms * 2, 256, 0, stream>>>(a, w, (int)pass);
+            cudaEventRecord(ev[3], stream);
+            cudaEventSynchronize(ev[3]);
+            for (int i = 0; i < 3; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); tsum[i] += ms; }
+            if (pass == 11) fprintf(stderr, "[bigd timing] NPART=%d BN=%d chains=%d D=%d: gemm_step %.3f ms, events %.3f ms, trajectory_end %.3f ms per pass (%d tiles on %d CTAs)\n",
+                                    NPART, BN, a.Nchain, D, tsum[0] / 8, tsum[1] / 8, tsum[2] / 8, ntiles, grid);
+            continue;
+        }
         bigd_gemm_step<NPART, BN><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, w, a.Nchain, D, (const float*)a.target.dt);
         cudaMemsetAsync(w.counters + 2, 0, 4, stream);
         bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
@@ -638,6 +675,7 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
             if (*running_h == 0) break;
         }
     }
+    if (timing) for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
     cudaFreeHost(running_h);
     if (rc == HMC_OK) HMC_CUDA_CHECK(cudaGetLastError());
     else hmc_set_error("large-D kernel: CUDA error in the pass loop: %s", cudaGetErrorString(cudaGetLastError()));

@@ -432,7 +432,7 @@ class HMC_sampler(sampler):
         ev1.record()
         ev1.synchronize()
         self.kernel_ms = ev0.elapsed_time(ev1)
-        if (a.flags & _L.FLAG_TC_FP16X2) and self.kernel in ("auto", "tc") and \
+        if (a.flags & _L.FLAG_TC_FP16X2) and self.kernel in ("auto", "tc") and D == 100 and \
                 int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0:
             # a start point left the range of the fp16 split (tensor-core kernel only): repeat with the bf16x3 split
             self.tc_precision = "bf16x3"
@@ -470,8 +470,6 @@ class HMC_sampler(sampler):
         import torch
         lib = _L.load()
         assert q_start.shape[0] == self.Nchain                                       # samplers.py:510
-        if not self._cov_p_identity:
-            raise NotImplementedError("NUTS CUDA kernel covers cov_p = I only (no CPU fallback)")
         if N_save_chain0 > 0:
             self.phi_q = []                                                          # samplers.py:514 (never filled)
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -492,6 +490,9 @@ class HMC_sampler(sampler):
         a = _L.NutsArgs()
         a.dtype = _L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64
         a.kernel = _L.KERNELS[self.kernel]
+        # (mirror of the library's AUTO rule, for reports: csrc/api.cu hmc_nuts_run)
+        self.nuts_kernel = "tc" if (self.kernel in ("auto", "tc") and self.dtype == "float32" and D == 100 and self.d_max <= 12) \
+            else "generic"
         a.Nchain, a.d_max, a.chain_id0 = Nc, int(self.d_max), self.chain_id0
         a.Niter, a.warm_up_num, a.thin_rate = self.Niter, self.warm_up_num, self.thin_rate
         a.on_dmax = 0 if self.on_dmax == "assert" else 1
