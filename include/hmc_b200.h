@@ -174,7 +174,9 @@ typedef struct hmc_nuts_args {
     double* dE_chain;
     void* state_q;
     double* state_eprev;
-    void* scratch;          /* [Nchain][2*(d_max+1)+7][D_pad] compute dtype: check-point stack (q,p), live and boundary points, cursors */
+    void* scratch;          /* [Nchain + 128][2*(d_max+1)+7][D_pad] compute dtype, zeroed before the first launch of a run: check-point
+                               stack (q,p), live and boundary points, cursors (row blocks by chain; the tensor-core kernel uses them by
+                               resident slot, hence the 128 extra) */
     unsigned long long* counters; /* [4]: leapfrog steps, doublings, energy-instability rejections, d_max hits */
     int32_t* status;        /* [Nchain] bit0: d_max exceeded; may be NULL */
     int64_t* n_leapfrog;    /* [Nchain] leapfrog steps per chain (accumulated); may be NULL */

@@ -375,8 +375,10 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) { return (f32x2)__flo
 // below the HBM time of a pass.  The two sums of squares of lag t = lag0 + k are those of lag0 (accumulated along the two
 // streams the kernel reads anyway) minus the first / last k terms, which are folded into the lag's accumulator (half each)
 // from 2 (NL - 1) re-read samples per chain.  The float32 cancellation costs ~1e-6 / (1 - rho_t) relative accuracy of V_t,
-// i.e. ~1e-6 absolute in rho_t (HMC_B200_DIAG_DIFF=1 selects the difference form above, e.g. for chains that drift far
-// within the window).  Same window / unrolling scheme as diag_variogram_f32x2_kernel.
+// i.e. ~1e-6 absolute in rho_t.  Same window / unrolling scheme as diag_variogram_f32x2_kernel.  MEASURED (6.55 GB stream,
+// 125-sample split chains, 16 lags): 2.53 ms against 2.20 ms for the difference form -- the per-chain prologue / epilogue
+// (masked first block, 30 re-read samples) and the two extra centring subtractions per step eat the saved arithmetic at
+// these chain lengths -- so the difference form stays the default and this kernel is selected with HMC_B200_DIAG_CROSS=1.
 template <int NL>
 __global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
                                                                     long stride_chain, int d0, int Dt, int spb, int lag0, int nlags,
@@ -581,7 +583,7 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
                 const int Dt = (D - d0 < 512) ? D - d0 : 512;
                 const int spb = 256 / (Dt / 2);
                 const size_t smem = sizeof(double) * NLP * Dt;
-                if (getenv("HMC_B200_DIAG_DIFF")) {
+                if (getenv("HMC_B200_DIAG_CROSS") == nullptr) {
                     HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_f32x2_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     diag_variogram_f32x2_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
                 } else {

@@ -42,6 +42,10 @@ __device__ __forceinline__ void s1_sync() { asm volatile("barrier.sync 5, %0;" :
 __device__ __forceinline__ void s1_arrive() { asm volatile("barrier.arrive 5, %0;" ::"n"(NT_S1) : "memory"); }
 __device__ __forceinline__ void grp_sync(int grp) { asm volatile("barrier.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
+// exp() of an energy difference: float32 expf (2 ulp) inside its range, float64 beyond (the weights overflow float32
+// at |dE| > 88; the guard allows 1000)
+__device__ __forceinline__ double nt_exp(double v) { return fabs(v) < 80.0 ? (double)expf((float)v) : exp(v); }
+
 struct NutsTcShared {
     float2 ex[TC_SPL][TC_M];                    // exchange 1: (q.g, p.p) per slice
     float2 chk[TC_SPL][NT_MAXCHK][TC_M];        // exchange 1: ((q - q_chk).p, (q - q_chk).p_chk) per slice and check point
@@ -58,6 +62,15 @@ struct NutsTcShared {
 #define NT_MARK(v) do { if (lane == 0) *reinterpret_cast<volatile int*>(&sh->mark[warp]) = (v); } while (0)
 #else
 #define NT_MARK(v)
+#endif
+// -DHMC_PROFILE_PHASES: cycles per phase of the worker loop, summed over warps (hmc_debug_nuts_tc_cycles)
+#ifdef HMC_PROFILE_PHASES
+__device__ unsigned long long g_nt_cycles[8];
+#define NP_T(x) const unsigned int x = (unsigned int)clock()
+#define NP_ADD(i, a, b) tph[i] += (b) - (a)
+#else
+#define NP_T(x)
+#define NP_ADD(i, a, b)
 #endif
 
 template <int PREC>
@@ -186,7 +199,11 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
     const double vconst = a.target.v_const;
     float* q_chain = (float*)a.q_chain;
 
-    auto scr_row = [&](int row) -> float* { return (float*)a.scratch + ((size_t)m * (R + 7) + row) * Dpad + j0; };
+    // check-point stack, live and boundary points: rows of the scratch block of this SLOT (not of the chain: the resident slots'
+    // 148 x 128 x 11.6 KB = 220 MB are re-used by every chain a slot runs, which keeps more of them in the 126 MB L2 than
+    // Nchain x 11.6 KB would); the cursor row R + 6 stays per chain (resume state of the injected draw streams)
+    const size_t slot_id = (size_t)blockIdx.x * TC_M + chain;
+    auto scr_row = [&](int row) -> float* { return (float*)a.scratch + (slot_id * (R + 7) + row) * Dpad + j0; };
     auto row_store = [&](int row, const float* v, float sgn) {
         float* dst = scr_row(row);
 #pragma unroll
@@ -273,7 +290,11 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
 
+#ifdef HMC_PROFILE_PHASES
+    unsigned int tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     while (true) {
+        NP_T(tA);
         // ===== A. the gradient pass issued after the previous S1 ===========================================================
         if (have_grad) {
             uint32_t done = 0;
@@ -298,6 +319,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
             if (*reinterpret_cast<volatile int*>(&sh->stop)) break;
         }
         NT_MARK(pn * 100 + 10);
+        NP_T(tB);
+        NP_ADD(0, tA, tB);
         // ===== B. consume the gradient: second half kick (phase STEP), partial energies, partial sub-tree check dots ==========
         const int pt = k + 1;                                   // number of the point the step reached (phase STEP)
         int nchk = 0;
@@ -355,9 +378,13 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
             }
         }
         NT_MARK(pn * 100 + 20);
+        NP_T(tB2);
+        NP_ADD(1, tB, tB2);
         __syncwarp();
         grp_sync(grp);
         NT_MARK(pn * 100 + 30);
+        NP_T(tC);
+        NP_ADD(2, tB2, tC);
         // ===== C. the chain's state machine, run identically by its four slice threads ===================================
         float r2a = 0.f, r2b = 0.f;                             // my partials for exchange 2
         bool finish = false, new_doubling = false, wait_k = false, traj_test = false;
@@ -432,7 +459,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
                     if (!reject) {                              // uniform progressive sampling (samplers.py:743-751)
                         const double E_prev_max = E_max_new;
                         E_max_new = fmax(E_prev_max, E_tmp);
-                        const double ex = exp(fabs(E_tmp - E_prev_max));
+                        const double ex = nt_exp(fabs(E_tmp - E_prev_max));
                         const bool new_max = E_tmp > E_prev_max;
                         const double numer = new_max ? 1.0 : ex;
                         pi_new = numer + (new_max ? ex : 1.0) * pi_new;
@@ -447,10 +474,10 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
                 // the new sub-trajectory is complete: extend the end (samplers.py:758-761), biased choice (:766-776, Q8)
                 if (u_dir == 0) { row_store(R + 4, x, 1.f); row_store(R + 5, p, 1.f); }
                 else { row_store(R + 2, x, 1.f); row_store(R + 3, p, 1.f); }
-                const double rb = exp(-(E_max_new - E_max_old)) * pi_old / pi_new;
+                const double rb = nt_exp(-(E_max_new - E_max_old)) * pi_old / pi_new;
                 const double E_max_old_prev = E_max_old;
                 E_max_old = fmax(E_max_old_prev, E_max_new);
-                pi_old = exp(-(E_max_new - E_max_old)) * pi_new + exp(-(E_max_old_prev - E_max_old)) * pi_old;
+                pi_old = nt_exp(-(E_max_new - E_max_old)) * pi_new + nt_exp(-(E_max_old_prev - E_max_old)) * pi_old;
                 const double A = fmin(1.0, rb);
                 const double ub = a.u_tape ? a.u_tape[(size_t)m * a.tape_u_stride + n_u++] : u_biased;
                 if (ub < A) {                                   // live_old <- live_new (each thread moves its own slice)
@@ -491,9 +518,13 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
         }
         sh->ex2[slice][chain] = make_float2(r2a, r2b);
         NT_MARK(pn * 100 + 40);
+        NP_T(tC2);
+        NP_ADD(3, tC, tC2);
         __syncwarp();
         grp_sync(grp);
         NT_MARK(pn * 100 + 50);
+        NP_T(tD);
+        NP_ADD(4, tC2, tD);
         // ===== D. second half of the state machine: results of exchange 2, trajectory ends, doublings, iteration ends ======
         {
             float e2a = 0.f, e2b = 0.f;
@@ -617,6 +648,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
             fetch_posted = true;
         }
         NT_MARK(pn * 100 + 64);
+        NP_T(tE);
+        NP_ADD(5, tD, tE);
         // ===== E. operand rows of the next gradient pass ====================================================================
         __syncwarp();
         put_half0<PREC>(acol, x);
@@ -628,11 +661,19 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
         NT_MARK(pn * 100 + 70);
+        NP_T(tF);
+        NP_ADD(6, tE, tF);
+#ifdef HMC_PROFILE_PHASES
+        tph[7] += 1;
+#endif
         s1_arrive();                                            // S1: rows written, alive flags posted (only the issuing warp waits there)
         have_grad = true;
         ++pn;
     }
 
+#ifdef HMC_PROFILE_PHASES
+    if (lane == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_nt_cycles[i], (unsigned long long)tph[i]);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
@@ -645,6 +686,16 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_nuts_tc_kernel(const hmc_nuts_ar
         }
     }
 }
+
+#ifdef HMC_PROFILE_PHASES
+}  // namespace
+extern "C" int hmc_debug_nuts_tc_cycles(unsigned long long* out8, int reset) {
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_nt_cycles, z, sizeof(z)); return 0; }
+    cudaMemcpyFromSymbol(out8, g_nt_cycles, sizeof(unsigned long long) * 8);
+    return 0;
+}
+namespace {
+#endif
 
 constexpr size_t nuts_tc_smem_bytes(int npart) {
     return (size_t)npart * TC_BPART + sizeof(float) * 2 * TC_KP + sizeof(NutsTcShared) + 64;

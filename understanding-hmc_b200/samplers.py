@@ -486,7 +486,8 @@ class HMC_sampler(sampler):
         counters = torch.zeros((4,), dtype=torch.int64, device=dev)
         status = torch.zeros((Nc,), dtype=torch.int32, device=dev)
         nleap = torch.zeros((Nc,), dtype=torch.int64, device=dev)
-        scratch = torch.zeros((Nc, 2 * (self.d_max + 1) + 7, tgt.D_pad), dtype=tdt, device=dev)
+        # (+128 row blocks: the tensor-core kernel indexes the stack rows by resident slot, 128 per CTA, not by chain)
+        scratch = torch.zeros((Nc + 128, 2 * (self.d_max + 1) + 7, tgt.D_pad), dtype=tdt, device=dev)
         a = _L.NutsArgs()
         a.dtype = _L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64
         a.kernel = _L.KERNELS[self.kernel]
