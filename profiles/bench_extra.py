@@ -31,7 +31,7 @@ if "diag" in which:
     for t in range(1, N):
         x[:, t] = 0.9 * x[:, t - 1] + 0.4359 * torch.randn((Nc, D), device="cuda", generator=g)
     n = N // 2
-    mom = torch.empty((3, D), dtype=torch.float64, device="cuda")
+    mom = torch.empty((4, D), dtype=torch.float64, device="cuda")
     buf = torch.empty((32, D), dtype=torch.float64, device="cuda")
     st = L.current_stream_ptr()
     ms_m = ev_time(lambda: L.check(lib.hmc_diag_moments(L.HMC_F32, L.ptr(x), Nc, n, D, x.stride(0), L.ptr(mom), st)))

@@ -12,7 +12,7 @@ x = torch.empty((Nc, N, D), dtype=torch.float32, device="cuda")
 x[:, 0] = torch.randn((Nc, D), device="cuda", generator=g)
 for t in range(1, N):
     x[:, t] = 0.9 * x[:, t - 1] + 0.4359 * torch.randn((Nc, D), device="cuda", generator=g)
-mom = torch.empty((3, D), dtype=torch.float64, device="cuda")
+mom = torch.empty((4, D), dtype=torch.float64, device="cuda")
 buf = torch.empty((32, D), dtype=torch.float64, device="cuda")
 st = L.current_stream_ptr()
 def timed(fn):
