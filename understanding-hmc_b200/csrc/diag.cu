@@ -375,12 +375,14 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) { return (f32x2)__flo
 // below the HBM time of a pass.  The two sums of squares of lag t = lag0 + k are those of lag0 (accumulated along the two
 // streams the kernel reads anyway) minus the first / last k terms, which are folded into the lag's accumulator (half each)
 // from 2 (NL - 1) re-read samples per chain.  The float32 cancellation costs ~1e-6 / (1 - rho_t) relative accuracy of V_t,
-// i.e. ~1e-6 absolute in rho_t.  Same window / unrolling scheme as diag_variogram_f32x2_kernel.  MEASURED (6.55 GB stream,
-// 125-sample split chains, 16 lags): 2.53 ms against 2.20 ms for the difference form -- the per-chain prologue / epilogue
-// (masked first block, 30 re-read samples) and the two extra centring subtractions per step eat the saved arithmetic at
-// these chain lengths -- so the difference form stays the default and this kernel is selected with HMC_B200_DIAG_CROSS=1.
-template <int NL>
-__global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
+// i.e. ~1e-6 absolute in rho_t (measured: n_eff of the Case 3c bench run equal to the difference form's to 1e-9).  Same
+// window / unrolling scheme as diag_variogram_f32x2_kernel.  MEASURED: with 16 lags per pass it is no faster than the
+// difference form (end-to-end step 250 vs 245 ms: both ride the HBM time of a pass at 400-sample chains; at 125 samples
+// the per-chain prologue / epilogue makes it slower, 2.53 vs 2.20 ms), and a 32-lags-in-one-pass instantiation (window +
+// accumulators = 128 registers, one 320-thread block per SM) fell into local memory and took 9.7 ms per 32 lags against
+// 4.4 ms for two 16-lag passes.  So the difference form stays the default; HMC_B200_DIAG_CROSS=1 selects this kernel.
+template <int NL, int H, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) diag_variogram_cross_kernel(const float* __restrict__ q, long Nchain, long n, int D, long pitch,
                                                                     long stride_chain, int d0, int Dt, int spb, int lag0, int nlags,
                                                                     double* __restrict__ out) {
     extern __shared__ double sm[];   // [NL][Dt]
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const floa
     __syncthreads();
     const int D2 = Dt >> 1;
     const int dp = threadIdx.x % D2, sl = threadIdx.x / D2;
-    constexpr int H = NL / 2;
+    constexpr int NHB = NL / H;                 // the streams are requested H steps at a time
     if (sl < spb) {
         const long nseries = 2 * Nchain;
         const long p2 = pitch >> 1;
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const floa
             long j0 = 0;
             if (nsteps > 0) {
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
+                for (int hb = 0; hb < NHB; ++hb) {
                     f32x2 xa[H], wn[H];
 #pragma unroll
                     for (int r = 0; r < H; ++r) {
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(256, 2) diag_variogram_cross_kernel(const floa
             }
             for (; j0 + NL <= nsteps; j0 += NL) {
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
+                for (int hb = 0; hb < NHB; ++hb) {
                     f32x2 xa[H], wn[H];
 #pragma unroll
                     for (int r = 0; r < H; ++r) { xa[r] = sub2(x[(lag0 + j0 + hb * H + r) * p2], c); wn[r] = sub2(x[(j0 + hb * H + r) * p2], c); }
@@ -574,8 +576,9 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
         return HMC_OK;
     }
     if (packed) {
-        // 16 lags per pass, two resident blocks per SM (the 32-lag window needs 190+ registers and leaves one block per SM
-        // waiting on its loads); a 32-lag request is two passes, the second one reads the samples from L2 / HBM again
+        const bool force_cross = getenv("HMC_B200_DIAG_CROSS") != nullptr;
+        // 16 lags per pass, two resident blocks per SM (the 32-lag difference-form window needs 190+ registers and leaves one
+        // block per SM waiting on its loads); a 32-lag request is two passes, the second one reads the samples again
         constexpr int NLP = 16;
         for (int l0 = 0; l0 < nlags; l0 += NLP) {
             const int nl = (nlags - l0 < NLP) ? nlags - l0 : NLP;
@@ -583,12 +586,13 @@ extern "C" int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, 
                 const int Dt = (D - d0 < 512) ? D - d0 : 512;
                 const int spb = 256 / (Dt / 2);
                 const size_t smem = sizeof(double) * NLP * Dt;
-                if (getenv("HMC_B200_DIAG_CROSS") == nullptr) {
+                if (!force_cross) {
                     HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_f32x2_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     diag_variogram_f32x2_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
                 } else {
-                    HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_variogram_cross_kernel<NLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    diag_variogram_cross_kernel<NLP><<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
+                    auto kern = diag_variogram_cross_kernel<NLP, 8, 256, 2>;
+                    HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kern<<<grid_for(2 * Nchain, spb, 2), 256, smem, stream>>>((const float*)q, Nchain, n, D, pitch, stride_chain, d0, Dt, spb, lag0 + l0, nl, out + (size_t)l0 * D);
                 }
             }
         }

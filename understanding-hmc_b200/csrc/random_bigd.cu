@@ -245,19 +245,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;");
             float hv = 0.f, hk = 0.f;
             if (live) {
-                for (int cb = half; cb < BN / EB; cb += 2) {
+                // The row segments of a column block are requested TWO blocks ahead (the epilogue was bound by the latency of these
+                // loads: ncu long-scoreboard 8.3 per issue, tensor pipe 26 %): registers va / vb hold the blocks in flight.
+                constexpr int NB = BN / EB / 2;                  // column blocks of this warp in a tile
+                const float* gsrc = ((sub & 1) ? w.x : w.p) + (size_t)nt * BN + col + (size_t)(row0 + (sub >> 1)) * D;
+                float* gdst = ((sub & 1) ? w.x : w.p) + (size_t)nt * BN + col + (size_t)(row0 + (sub >> 1)) * D;
+                float* sdst = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
+                float va[16], vb[16];
+                auto request = [&](float (&v)[16], int b) {
+                    const float* src = gsrc + (half + 2 * b) * EB;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + (size_t)(2 * i) * D);
+                };
+                auto block = [&](float (&v)[16], int b) {
+                    const int cb = half + 2 * b;
                     const int c0 = nt * BN + cb * EB;
-                    // row segments -> shared: lanes (sub 0, 2): momentum of rows i, i + 1; (sub 1, 3): position; all 16 loads in flight
-                    {
-                        const float* src = ((sub & 1) ? w.x : w.p) + c0 + col + (size_t)(row0 + (sub >> 1)) * D;
-                        float* dst = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
-                        float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + (size_t)(2 * i) * D);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) dst[2 * i * (EB + 1)] = v[i];
-                    }
+                    for (int i = 0; i < 16; ++i) sdst[2 * i * (EB + 1)] = v[i];
                     __syncwarp();
+                    if (b + 2 < NB) request(v, b + 2);          // this buffer's next block, in flight during the arithmetic below
                     uint32_t gv[8];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                                  : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7])
@@ -284,9 +290,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                         for (int pt = 0; pt < NPART; ++pt) Hs[(pt * 32 + lane) * (EB / 2 + 1) + j] = h[pt];
                     }
                     __syncwarp();
-                    // shared -> row segments
-                    {
-                        float* dst = ((sub & 1) ? w.x : w.p) + c0 + col + (size_t)(row0 + (sub >> 1)) * D;
+                    {   // shared -> row segments
+                        float* dst = gdst + cb * EB;
                         const float* src = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) __stcs(dst + (size_t)(2 * i) * D, src[2 * i * (EB + 1)]);
@@ -302,6 +307,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                         }
                     }
                     __syncwarp();
+                };
+                request(va, 0);
+                if (NB > 1) request(vb, 1);
+                for (int b = 0; b < NB; b += 2) {
+                    block(va, b);
+                    if (b + 1 < NB) block(vb, b + 1);
                 }
             }
             if (chain < Nchain) {
