@@ -331,9 +331,13 @@ def secondary_measurements(torch, dist, S, U, L, lib, rank, world, dev, log):
             xs = torch.empty((Nc, 50, D), dtype=torch.float32, device=dev).normal_()
             buf = torch.empty((40, D), dtype=torch.float64, device=dev)
             st = L.current_stream_ptr()
+            abuf = torch.empty((124, D), dtype=torch.float64, device=dev)
+            ws = torch.empty((int(lib.hmc_diag_variogram_all_workspace_bytes(125, D)) // 8,), dtype=torch.float64, device=dev)
             cases = [("diag_moments", x, lambda: lib.hmc_diag_moments(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, L.ptr(buf), st), 1.0),
                      ("diag_variogram_32lags", x, lambda: lib.hmc_diag_variogram(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, 33, 32, L.ptr(buf), st), 2.0),
                      ("diag_variogram_16lags", x, lambda: lib.hmc_diag_variogram(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, 33, 16, L.ptr(buf), st), 1.0),
+                     ("diag_variogram_all_lags_fft", x, lambda: lib.hmc_diag_variogram_all(L.HMC_F32, L.ptr(x), Nc, 125, D, 250 * D, 124, L.ptr(abuf),
+                                                                                           L.ptr(ws), ws.numel() * 8, st), 1.0),
                      ("diag_short_series", xs, lambda: lib.hmc_diag_short_series(L.HMC_F32, L.ptr(xs), Nc, 25, D, 50 * D, 24, L.ptr(buf), L.ptr(buf[5:]), st), 1.0)]
             for name, arr, fn, passes in cases:
                 for _ in range(2):

@@ -212,6 +212,16 @@ int hmc_diag_variogram(int32_t dtype, const void* q, int64_t Nchain, int64_t n, 
 int hmc_diag_short_series(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
                           int32_t nlags, double* out4xD, double* out_lags, void* cuda_stream);
 
+/* Every lag at once (float32 streams, 32 < n <= 512, D % 4 == 0, 16-byte aligned rows; anything else returns
+ * HMC_E_UNSUPPORTED and the caller stays with hmc_diag_variogram): out[t - 1][D] for t in [1, nlags], nlags <= n - 1, the same
+ * numerators as hmc_diag_variogram, from ONE pass over the samples -- a 1024-point FFT per (chain, dimension) carrying both
+ * split chains as real and imaginary part, power spectra summed over chains in float64, the cosine transform and the edge
+ * sums of squares finished by a small float64 kernel (csrc/diag_fft.cu; utils.py:141-152 calls variogram once per lag).
+ * `workspace`: device scratch of hmc_diag_variogram_all_workspace_bytes(n, D) bytes, zeroed by the call. */
+int64_t hmc_diag_variogram_all_workspace_bytes(int64_t n, int32_t D);
+int hmc_diag_variogram_all(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
+                           int32_t nlags, double* out_nlags_x_D, void* workspace, int64_t workspace_bytes, void* cuda_stream);
+
 /*
  * Start points on the device: replaces utils.start_pts (utils.py:204-209, np.random.multivariate_normal(q0, cov0, size)).
  * out[m][:] = q0 + Lc z_m with z_m ~ N(0, I) from Philox keyed by (seed, chain_id0 + m), so the points do not depend on

@@ -21,11 +21,14 @@ constexpr uint32_t TC_ACOL = 128;               // first TMEM column of the A pa
 constexpr uint32_t TC_APITCH = 64;              // TMEM columns per A part (56 used: K/2)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// named barriers: 1..4 = the four warps of a 32-chain group, 5 = workers + issuing warp
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 5, %0;" ::"n"(TC_NT) : "memory"); }
+// named barriers: 1..4 = the four warps of a 32-chain group, 5 = workers + issuing warp.  The non-".aligned" PTX forms
+// (barrier.sync / barrier.arrive count threads and do not require a converged warp): the worker loops are full of per-lane
+// branches, and with the aligned forms the tensor-core NUTS kernel was observed to get a warp one barrier out of step
+// (profiles/r2_nuts_tc_barrier_note.md).
+__device__ __forceinline__ void bar_all() { asm volatile("barrier.sync 5, %0;" ::"n"(TC_NT) : "memory"); }
 // the workers only ARRIVE at S1 (they never wait for each other there: what they need next is the MMA, through its mbarrier)
-__device__ __forceinline__ void bar_all_arrive() { asm volatile("bar.arrive 5, %0;" ::"n"(TC_NT) : "memory"); }
-__device__ __forceinline__ void bar_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
+__device__ __forceinline__ void bar_all_arrive() { asm volatile("barrier.arrive 5, %0;" ::"n"(TC_NT) : "memory"); }
+__device__ __forceinline__ void bar_group(int grp) { asm volatile("barrier.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;

@@ -8,6 +8,7 @@ and -- when the optional libraries are installed -- ``plt``, ``mpl``, ``Ellipse`
 
 ``convergence_stats`` runs on the GPU (csrc/diag.cu through the C-ABI) -- there is no CPU implementation here.
 """
+import os as _os
 import time  # noqa: F401  (re-exported, utils.py:3)
 
 import numpy as np
@@ -105,7 +106,10 @@ def _finish_n_eff(var, V_rows, m, n, state):
 ROW_SHIFT, ROW_COUNT, ROW_LAGS = 3, 4, 5        # layout of the packed statistics buffer [5 + lag_chunk][D]
 
 
-def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32, device=None):
+FFT_MIN_N = 192        # split chains at least this long take the all-lags FFT pass straight away (see _stats_from_partials)
+
+
+def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, lag_chunk=32, device=None, all_lags_fn=None):
     """Rhat / n_eff from per-rank partial sums (utils.py:107-157).
 
     ``moments_fn(buf)`` fills the float64 buffer ``buf`` [5 + lag_chunk][D]: rows 0..2 = sum_j std_j, sum_j (mean_j - c),
@@ -118,7 +122,12 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
     and one D2H copy per call for short series, plus one all-reduce per further lag chunk; the only exchange step on the
     whole path.  Ranks are combined on the host: counts and lag sums add up; the between-chain sum of squares
     uses the pairwise update  M2 = sum_r M2_r + sum_r m_r (mean_r - mean)^2  (the two-round form of SURVEY 8e without a
-    second round).  Everything after that is O(lags * D) host arithmetic."""
+    second round).  Everything after that is O(lags * D) host arithmetic.
+
+    ``all_lags_fn(buf)`` (optional) fills ``buf`` [n - 1][D] with the numerators of EVERY lag in one pass over the samples
+    (csrc/diag_fft.cu: one FFT per chain and dimension, a fixed cost per chain).  Long split chains (n >= FFT_MIN_N) use it
+    straight away; shorter ones try one windowed chunk first (a well-mixed chain ends within it) and switch when the
+    truncation rule has not fired.  Sharded runs all-reduce that one buffer."""
     import torch
     import torch.distributed as dist
     distributed = dist.is_available() and dist.is_initialized() and (group is not False)
@@ -152,6 +161,13 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
         nl = min(lag_chunk, max_lag - lag0 + 1)
         if lag0 == 1 and nfilled:
             rows = host[:, ROW_LAGS:ROW_LAGS + nl].sum(axis=0)
+        elif all_lags_fn is not None and (lag0 > 1 or n >= FFT_MIN_N):
+            abuf = _scratch("all_lags", (max_lag, D), torch.float64, device)
+            all_lags_fn(abuf)
+            if distributed:
+                dist.all_reduce(abuf, group=grp)
+            rows = abuf[lag0 - 1:].cpu().numpy()
+            nl = max_lag - lag0 + 1
         else:
             if vbuf is None:
                 vbuf = _scratch("lags", (lag_chunk, D), torch.float64, device)
@@ -206,7 +222,16 @@ def _device_stats(x, n, group=None, lag_chunk=32):
         _L.check(lib.hmc_diag_variogram(dtype, _L.ptr(x), Nchain, n, D, stride_chain, lag0, nl, _L.ptr(buf),
                                         _L.current_stream_ptr()))
 
-    return _stats_from_partials(moments_fn, variogram_fn, n, D, 2 * Nchain, group=group, lag_chunk=lag_chunk, device=x.device)
+    all_lags_fn = None
+    if (x.dtype == torch.float32 and 32 < n <= 512 and D % 4 == 0 and stride_chain % 4 == 0 and x.data_ptr() % 16 == 0
+            and _os.environ.get("HMC_B200_DIAG_NO_FFT") is None):
+        def all_lags_fn(buf):
+            ws = _scratch("fft_ws", (int(lib.hmc_diag_variogram_all_workspace_bytes(n, D)) // 8,), torch.float64, x.device)
+            _L.check(lib.hmc_diag_variogram_all(dtype, _L.ptr(x), Nchain, n, D, stride_chain, n - 1, _L.ptr(buf), _L.ptr(ws),
+                                                ws.numel() * 8, _L.current_stream_ptr()))
+
+    return _stats_from_partials(moments_fn, variogram_fn, n, D, 2 * Nchain, group=group, lag_chunk=lag_chunk, device=x.device,
+                                all_lags_fn=all_lags_fn)
 
 
 def convergence_stats(q_chain, thin_rate=5, warm_up_num=0, group=None):
