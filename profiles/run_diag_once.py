@@ -25,6 +25,11 @@ gb = Nc * N * D * 4 / 1e9
 t_m = timed(lambda: L.check(lib.hmc_diag_moments(L.HMC_F32, L.ptr(x), Nc, n, D, x.stride(0), L.ptr(mom), st)))
 t_v = timed(lambda: L.check(lib.hmc_diag_variogram(L.HMC_F32, L.ptr(x), Nc, n, D, x.stride(0), 1, 32, L.ptr(buf), st)))
 print("long series n=%d: %.2f GB  moments %.3f ms = %.0f GB/s | variogram (32 lags) %.3f ms = %.0f GB/s algorithmic" % (n, gb, t_m, gb / t_m * 1e3, t_v, gb / t_v * 1e3))
+if n <= 512:
+    abuf = torch.empty((n - 1, D), dtype=torch.float64, device="cuda")
+    ws = torch.empty((int(lib.hmc_diag_variogram_all_workspace_bytes(n, D)) // 8,), dtype=torch.float64, device="cuda")
+    t_f = timed(lambda: L.check(lib.hmc_diag_variogram_all(L.HMC_F32, L.ptr(x), Nc, n, D, x.stride(0), n - 1, L.ptr(abuf), L.ptr(ws), ws.numel() * 8, st)))
+    print("all lags (FFT) n=%d: %.3f ms = %.0f GB/s algorithmic, %.1f ns per (chain, dimension) transform" % (n, t_f, gb / t_f * 1e3, t_f * 1e6 / (Nc * D)))
 ns = 25                                  # the bench's short series: 50 stored samples per chain
 xs = x[:, :2 * ns]
 gbs = Nc * 2 * ns * D * 4 / 1e9

@@ -49,8 +49,9 @@ def test_convergence_stats_on_reference_chains(name):
 @pytest.mark.parametrize("shape", [(37, 400, 100, 0.95, 0.0), (130, 125, 8, 0.6, 3.0), (9, 512, 4, 0.99, -40.0), (3, 33, 12, 0.5, 0.0)])
 def test_all_lags_fft_equals_windowed_numerators(shape):
     """hmc_diag_variogram_all (one FFT per chain and dimension) against hmc_diag_variogram on the float64 copy of the same
-    float32 stream, every lag 1..n-1: relative to the lag's own numerator (float32 transform: 2e-5 with the cancellation of
-    strongly correlated series), and against the plain numpy sum."""
+    float32 stream, every lag 1..n-1, and against the plain numpy sum.  The float32 transform leaves an error relative to
+    the series' energy (the edge sums of squares, of which a strongly correlated series' small-lag numerators are a small
+    difference): bound 2e-6 of the largest numerator, measured 2e-7 to 3e-7."""
     import torch
     import hmc_b200_lib as L
     Nchain, n, D, phi, offset = shape
@@ -71,8 +72,8 @@ def test_all_lags_fft_equals_windowed_numerators(shape):
     xs = x32.astype(np.float64).reshape(Nchain * 2, n, D)
     for t in (1, 2, n // 2, n - 1):
         np.testing.assert_allclose(want[t - 1], np.sum((xs[:, t:] - xs[:, :-t]) ** 2, axis=(0, 1)), rtol=1e-12)
-    scale = want[: max(1, n // 2)].max(axis=0)                      # numerators of long lags shrink with n - t
-    assert np.max(np.abs(got - want) / np.maximum(want, 1e-3 * scale)) < 2e-5
+    scale = want.max(axis=0)
+    assert np.max(np.abs(got - want) / scale) < 2e-6
     # a second call re-zeroes its workspace
     L.check(lib.hmc_diag_variogram_all(L.HMC_F32, L.ptr(x), Nchain, n, D, 2 * n * D, n - 1, L.ptr(out), L.ptr(ws), ws.numel() * 8, st))
     torch.cuda.synchronize()
