@@ -45,7 +45,8 @@ enum {
                                the FFMA2 kernel, else the generic one */
     HMC_KERNEL_GENERIC = 1, /* one warp per chain, any D <= 1024, float or double (parity workhorse) */
     HMC_KERNEL_FAST = 2,    /* FP32 FFMA2 register-tile kernel, 20 < D <= 128, identity momentum metric */
-    HMC_KERNEL_TC = 3,      /* tcgen05 tensor-core kernel (bf16x3 / fp16x2 split, fp32 accumulate in TMEM), D = 100, identity metric */
+    HMC_KERNEL_TC = 3,      /* tcgen05 tensor-core kernel (bf16x3 / fp16x2 split, fp32 accumulate in TMEM), D <= 100 and a multiple of 4
+                               (smaller targets run zero padded in the 100-wide tile; AUTO picks it from D = 52), identity metric */
     HMC_KERNEL_BIGD = 4     /* large D (multiple of 256): one tcgen05 GEMM over all chains per leapfrog step, operands by TMA, the
                                leapfrog update fused into the epilogue; needs hmc_random_args.workspace */
 };

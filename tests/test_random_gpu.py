@@ -351,6 +351,46 @@ def test_tc_kernel_very_short_trajectories_match_generic():
     np.testing.assert_allclose(F.dE_chain[:, 1:, 0], np.diff(F.E_chain[:, :, 0], axis=1), rtol=0, atol=2e-4)
 
 
+@pytest.mark.parametrize("D,rho,uniform_dt", [(96, 0.95, True), (64, 0.9, True), (52, 0.5, False), (8, 0.3, True)])
+def test_tc_kernel_smaller_dimensions_match_generic(D, rho, uniform_dt):
+    """Targets with D < 100 (a multiple of 4) run zero padded in the tensor-core kernel's 100-wide tile: same Philox draws as
+    the generic kernel => same trajectory lengths, the same first trajectory (rel 1e-5), matching acceptance and energies,
+    with warm-up, thinning, iteration blocks, a chain-id offset, slot refill (more chains than one CTA's slots) and the
+    chain-0 trace.  "auto" picks the tensor-core kernel from D = 52 up."""
+    import samplers as S
+    Nchain, Niter = 2500, 9
+    mu = np.linspace(-1, 1, D)
+    spec = S.MVNSpec.from_cov(mu, O.equicorrelated_cov(D, rho))
+    q_start = (np.random.RandomState(D).standard_normal((Nchain, D)) * 1.2 + mu).astype(np.float32)
+    dt = 0.1 if uniform_dt else 0.05 + 0.1 * np.arange(D) / D
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=2, warm_up_num=3, sampler_type="Random", dt=dt, L_low=4,
+              L_high=11, dtype="float32", seed=5, target=spec)
+    F = S.HMC_sampler(D, None, None, kernel="tc" if D < 52 else "auto", iter_block=4, **kw)
+    F.gen_sample(q_start, N_save_chain0=3, verbose=False, quiet=True)
+    G = S.HMC_sampler(D, None, None, kernel="generic", **kw)
+    G.gen_sample(q_start, N_save_chain0=3, verbose=False, quiet=True)
+    assert F.sum_L == G.sum_L
+    assert F.q_chain.shape == G.q_chain.shape == (Nchain, 1 + (Niter - 3) // 2, D)
+    amp = np.linalg.norm(q_start.astype(float) - mu, axis=1) + 1.0
+    rel = np.linalg.norm(F.q_chain[:, 0] - G.q_chain[:, 0], axis=1) / amp          # index 0: overwritten at i = warm (3 iterations in)
+    assert np.quantile(rel, 0.9) < 1e-4
+    rel_last = np.linalg.norm(F.q_chain[:, -1] - G.q_chain[:, -1], axis=1) / amp
+    assert np.mean(rel_last < 1e-3) > 0.9
+    assert abs(F.accept_R - G.accept_R) < 1e-2
+    same = rel_last < 1e-3
+    np.testing.assert_allclose(F.E_chain[same, :, 0], G.E_chain[same, :, 0], rtol=2e-4, atol=2e-3)
+    assert [len(x) for x in F.phi_q] == [len(x) for x in G.phi_q]
+    np.testing.assert_allclose(F.phi_q[0], G.phi_q[0], rtol=0, atol=1e-4)
+    assert np.all(np.isfinite(F.q_chain))
+    # one iteration from the same start, no warm-up: the first trajectory itself
+    kw1 = dict(kw, Niter=1, thin_rate=1, warm_up_num=0)
+    F1 = S.HMC_sampler(D, None, None, kernel="tc", **kw1); F1.gen_sample(q_start, verbose=False, quiet=True)
+    G1 = S.HMC_sampler(D, None, None, kernel="generic", **kw1); G1.gen_sample(q_start, verbose=False, quiet=True)
+    rel1 = np.linalg.norm(F1.q_chain[:, 1] - G1.q_chain[:, 1], axis=1) / amp
+    assert np.quantile(rel1, 0.995) < 1e-5
+    np.testing.assert_allclose(F1.E_chain[:, 0, 0], G1.E_chain[:, 0, 0], rtol=2e-5)
+
+
 @pytest.mark.parametrize("D,rho", [(128, 0.9), (101, 0.5), (64, 0.95), (33, 0.3), (24, 0.0)])
 def test_fast_kernel_other_dimensions_match_generic(D, rho):
     """The fused kernel's other tile shapes (20 < D <= 128; padded dimensions, per-dimension dt when D is odd):

@@ -62,8 +62,11 @@ extern "C" int hmc_random_run(const hmc_random_args* args, void* cuda_stream) {
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     int kernel = a.kernel;
     const char* why = "";
-    if (kernel == HMC_KERNEL_AUTO)                  // tensor-core kernel where it applies, then the FFMA kernel, then the generic one
-        kernel = hmc_random_tc_supported(a, &why) ? HMC_KERNEL_TC
+    // tensor-core kernel where it applies and pays (its 100-wide tile does the work of D = 100 whatever D is: ~6.4e9
+    // gradient-evals/s; the FFMA kernel's rate grows as 1/D^2 and overtakes it below D ~ 50), then the large-D GEMM path, then
+    // the FFMA kernel, then the generic one
+    if (kernel == HMC_KERNEL_AUTO)
+        kernel = (a.target.D >= 52 && hmc_random_tc_supported(a, &why)) ? HMC_KERNEL_TC
                  : (a.workspace && hmc_random_bigd_supported(a, &why)) ? HMC_KERNEL_BIGD
                  : hmc_random_fast_supported(a, &why) ? HMC_KERNEL_FAST : HMC_KERNEL_GENERIC;
     if (kernel == HMC_KERNEL_BIGD) {

@@ -77,13 +77,17 @@ struct TcGen {
     const int32_t* L_tape;
     const double* u_tape;
     int Niter, L_low, L_high;
+    int D;                              // dimensions of the target (<= TC_ND; the rest of the 100-wide rows is zero padding)
 };
 
 // Warp-cooperative momentum draw for one chain: lane sl < 25 draws the normals of dims 4*sl..4*sl+3 into `stage`,
-// lane 25 the scalars of the iteration.  Same arithmetic as hmc_normal4 / hmc_scalar_draws.
+// lane 25 the scalars of the iteration.  Same arithmetic as hmc_normal4 / hmc_scalar_draws.  A target with D < 100 uses the
+// first D / 4 lanes; the padded dimensions keep momentum zero (their force rows are zero too), so they never move.
+template <bool DFULL>
 __device__ __forceinline__ void tc_gen(const TcGen& g, long m, uint64_t gid, int iter, int lane, float* stage, float* sumsq,
                                        int* L, float* lnu) {
-    constexpr int D = TC_ND, nslot = TC_ND / 4;
+    constexpr int nslot = TC_ND / 4;
+    const int D = DFULL ? TC_ND : g.D;
     float s = 0.f;
     int Lv = 1;
     float lv = 0.f;
@@ -104,7 +108,7 @@ __device__ __forceinline__ void tc_gen(const TcGen& g, long m, uint64_t gid, int
         const float a1 = ((float)(r.y >> 8) * 5.9604644775390625e-08f - 0.5f) * 6.283185307179586f;
         const float a2 = ((float)(r.w >> 8) * 5.9604644775390625e-08f - 0.5f) * 6.283185307179586f;
         const float4 z = make_float4(r1 * __cosf(a1), r1 * __sinf(a1), r2 * __cosf(a2), r2 * __sinf(a2));
-        if (lane < nslot) {
+        if (4 * lane < D) {
             *reinterpret_cast<float4*>(stage + 4 * lane) = z;
             s = z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
         }
@@ -142,9 +146,12 @@ struct TcShared {                       // small per-chain arrays in shared memo
 constexpr int OUT_SAMPLE = 1 << 29, OUT_STATE = 1 << 30;   // copy the chain's start-point row to q_chain[m][idx] / to state_q[m]
 constexpr int REQ_INIT0 = 1 << 30;      // request flag: also draw the chain-start momentum (iteration 0, K only)
 
-template <bool UDT, int PREC>
+template <bool UDT, int PREC, bool DFULL>
 __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_random_args a, unsigned int* __restrict__ queue, int* progress, int nsb, int SB) {
-    constexpr int D = TC_ND, KP = TC_KP, KC = TC_KC;
+    constexpr int KP = TC_KP, KC = TC_KC;
+    // DFULL: D == TC_ND at compile time (the benchmark path keeps its constant addressing); otherwise D <= TC_ND, D % 4 == 0
+    // and dimensions D..111 are zero padding (force, mu, dt, rows)
+    const int D = DFULL ? TC_ND : a.target.D;
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int NPART = TcPrec<PREC>::NPART;
     unsigned char* Bp = smem;                                   // NPART parts [KC][112] 16-byte chunks
@@ -209,6 +216,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             mu_s[t] = (t < D) ? ((const float*)a.target.mu)[t] : 0.f;
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
+        for (int t = tid; t < 2 * TC_M * TC_SROW; t += TC_NT) stage_all[t] = 0.f;      // staging and start-point rows (padding stays zero)
         for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; sh->out_req[2][t] = 0; sh->out_req[3][t] = 0; }
         if (tid < 16) sh->galive[tid >> 2][tid & 3] = 1;
         if (tid == 0) sh->stop = 0;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     const float vconst = (float)a.target.v_const;
     TcGen ga;
     ga.seed = a.seed; ga.p_tape = a.p_tape; ga.L_tape = a.L_tape; ga.u_tape = a.u_tape;
-    ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high;
+    ga.Niter = a.Niter; ga.L_low = a.L_low; ga.L_high = a.L_high; ga.D = D;
 
     if (slice >= TC_SPL) {
         // ===== the issuing warpgroup: hands its registers to the workers (per scheduler: 4 x 112 + 24 registers x 32 lanes
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     while (todo) {
                         const int cs = g * 32 + __ffs(todo) - 1;
                         todo &= todo - 1;
-                        if (k == cw && lane < TC_ND / 4) {
+                        if (k == cw && 4 * lane < D) {
                             const int r = sh->out_req[rp][cs];
                             const size_t mc = (size_t)sh->out_m[rp][cs];
                             const float4 d4 = *reinterpret_cast<const float4*>(q0_s + cs * TC_SROW + 4 * lane);
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const float* src = (fresh ? (const float*)a.q_start : q0g) + mc * D + j0;       // unit / launch left in state_q
 #pragma unroll
                     for (int c = 0; c < 7; ++c) {
-                        if (c < nch4) {
+                        if (c < nch4 && j0 + 4 * c < D) {
                             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + 4 * c));
                             const float4 mu4 = *reinterpret_cast<const float4*>(mu_s + j0 + 4 * c);
                             if (fresh) *reinterpret_cast<float4*>(q_chain + mc * Lrow * D + j0 + 4 * c) = v;
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                 float ks = 0.f, ln = 0.f; int Lx = 1;
                 // a chain start also needs the momentum of iteration 0 (samplers.py:415, K only): one call site, two turns
                 for (int turn = (rq & REQ_INIT0) ? 0 : 1; turn < 2; ++turn) {
-                    tc_gen(ga, m_s, gid, turn ? (rq & ~REQ_INIT0) : 0, lane, st, &ks, &Lx, &ln);
+                    tc_gen<DFULL>(ga, m_s, gid, turn ? (rq & ~REQ_INIT0) : 0, lane, st, &ks, &Lx, &ln);
                     if (turn == 0) { if (lane == 0) sh->gK0[cs] = ks; __syncwarp(); }
                 }
                 if (lane == 0) {
@@ -719,19 +727,25 @@ static_assert(tc_smem_bytes(3) <= 232448, "shared memory of the tensor-core kern
 bool hmc_random_tc_supported(const hmc_random_args& a, const char** why) {
     if (a.dtype != HMC_F32) { *why = "float32 only"; return false; }
     if (a.target.Mit || a.target.Pt || a.target.Lct) { *why = "identity momentum metric only"; return false; }
-    if (a.target.D != TC_ND) { *why = "D == 100 in this build"; return false; }
+    if (a.target.D > TC_ND || a.target.D < 4 || (a.target.D % 4) != 0) { *why = "D <= 100 and a multiple of 4 (smaller targets run zero padded in the 100-wide tile)"; return false; }
     if (a.iter_end <= a.iter_begin) { *why = "needs at least one iteration"; return false; }
     if (!a.state_g) { *why = "state_g scratch required"; return false; }
     return true;
 }
 
-template <bool UDT, int PREC>
-static int tc_launch(const hmc_random_args& a, int grid, unsigned int* queue, int* progress, int nsb, int SB, cudaStream_t stream) {
+template <bool UDT, int PREC, bool DFULL>
+static int tc_launch_d(const hmc_random_args& a, int grid, unsigned int* queue, int* progress, int nsb, int SB, cudaStream_t stream) {
     const size_t smem = tc_smem_bytes(TcPrec<PREC>::NPART);
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(hmc_random_tc_kernel<UDT, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hmc_random_tc_kernel<UDT, PREC><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(hmc_random_tc_kernel<UDT, PREC, DFULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hmc_random_tc_kernel<UDT, PREC, DFULL><<<grid, TC_NT, smem, stream>>>(a, queue, progress, nsb, SB);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
+}
+
+template <bool UDT, int PREC>
+static int tc_launch(const hmc_random_args& a, int grid, unsigned int* queue, int* progress, int nsb, int SB, cudaStream_t stream) {
+    return a.target.D == TC_ND ? tc_launch_d<UDT, PREC, true>(a, grid, queue, progress, nsb, SB, stream)
+                               : tc_launch_d<UDT, PREC, false>(a, grid, queue, progress, nsb, SB, stream);
 }
 
 int hmc_random_run_tc(const hmc_random_args& a, cudaStream_t stream) {
