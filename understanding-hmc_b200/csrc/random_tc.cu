@@ -139,6 +139,8 @@ struct TcShared {                       // small per-chain arrays in shared memo
     float gK[TC_M], gK0[TC_M], glnu[TC_M];   // results of the momentum draw
     int gL[TC_M];
     int galive[4][4];                   // per pass number & 3 and group: some slot still has (or wants) a chain
+    unsigned long long cnt[4][TC_M];    // per-slot counters (accepted warm-up / kept iterations, sum L, sum L^2): shared memory, not
+                                        // registers -- every register of the workers counts (a build with 17 more spilled words ran 6 % slower)
     int stop;                           // set by the issuing warp when the CTA is done (the workers see it after the MMA wait)
     unsigned int fmax_bits;             // bit pattern of max |F| (set-up only: scale of the fp16 B parts)
 };
@@ -217,7 +219,8 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
             dt_s[t] = (t < D) ? ((const float*)a.target.dt)[t] : 0.f;
         }
         for (int t = tid; t < 2 * TC_M * TC_SROW; t += TC_NT) stage_all[t] = 0.f;      // staging and start-point rows (padding stays zero)
-        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; sh->out_req[2][t] = 0; sh->out_req[3][t] = 0; }
+        for (int t = tid; t < TC_M; t += TC_NT) { sh->mode[t] = MODE_IDLE; sh->cmd[t] = 0; sh->req[t] = 0; sh->cm[t] = 0; sh->drawn[t] = -1; sh->out_req[0][t] = 0; sh->out_req[1][t] = 0; sh->out_req[2][t] = 0; sh->out_req[3][t] = 0;
+                                                 sh->cnt[0][t] = 0ull; sh->cnt[1][t] = 0ull; sh->cnt[2][t] = 0ull; sh->cnt[3][t] = 0ull; }
         if (tid < 16) sh->galive[tid >> 2][tid & 3] = 1;
         if (tid == 0) sh->stop = 0;
     }
@@ -360,7 +363,6 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     int pn = 0;                      // pass number
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
     float E_init = 0.f, E_prev = 0.f, lnu = 0.f;
-    unsigned long long n_acc_warm = 0, n_acc_post = 0, n_sumL = 0, n_sumL2 = 0;   // 64-bit: sum L^2 of a long launch exceeds 2^32
     uint32_t phase = 0;
     bool have_grad = false;          // a gradient pass has been issued and its accumulator is to be consumed
 #ifdef HMC_PROFILE_PHASES
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     // the draws of this iteration (requested at least two passes ago): samplers.py:431, 441
                     const float Knew = 0.5f * sh->gK[chain];
                     L = sh->gL[chain]; lnu = sh->glnu[chain];
-                    n_sumL += (unsigned long long)L; n_sumL2 += (unsigned long long)(L * L);
+                    sh->cnt[2][chain] += (unsigned long long)L; sh->cnt[3][chain] += (unsigned long long)(L * L);   // 64-bit: sum L^2 of a long launch exceeds 2^32
                     if (tr && it <= a.N_save_chain0) a.phi_len[it - 1] = L + 1;                     // samplers.py:444
                     if (init) {                                                 // samplers.py:416-420
                         const float E0 = V + 0.5f * sh->gK0[chain];
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     E_prev = E_init;                                            // samplers.py:460
                     const bool accepted = (dE < 0.f) || (lnu < -dE);            // samplers.py:462
                     const bool keep = it >= a.warm_up_num;
-                    if (accepted) { if (keep) n_acc_post++; else n_acc_warm++; cmd |= CMD_STORE_Q0; }
+                    if (accepted) { sh->cnt[keep ? 1 : 0][chain] += 1ull; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
                     if (keep) oreq = ((int)((long)(thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate) % Lrow) + 1) | OUT_SAMPLE;
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
@@ -695,8 +697,9 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     if (a.counters) {
-        const unsigned long long c0 = warp_sum<unsigned long long>(n_acc_warm), c1 = warp_sum<unsigned long long>(n_acc_post);
-        const unsigned long long c2 = warp_sum<unsigned long long>(n_sumL), c3 = warp_sum<unsigned long long>(n_sumL2);
+        const bool mine = slice == 0;                           // (the bookkeeping threads' own slots; nobody writes them any more)
+        const unsigned long long c0 = warp_sum<unsigned long long>(mine ? sh->cnt[0][chain] : 0ull), c1 = warp_sum<unsigned long long>(mine ? sh->cnt[1][chain] : 0ull);
+        const unsigned long long c2 = warp_sum<unsigned long long>(mine ? sh->cnt[2][chain] : 0ull), c3 = warp_sum<unsigned long long>(mine ? sh->cnt[3][chain] : 0ull);
         if (lane == 0) {
             atomicAdd(a.counters + 0, c0); atomicAdd(a.counters + 1, c1);
             atomicAdd(a.counters + 2, c2); atomicAdd(a.counters + 3, c3);
