@@ -17,3 +17,14 @@ def test_case_script_runs_unchanged(tmp_path):
     assert "After warm up:" in out and "Completed." in out
     assert "Total number of samples: %d" % (80 * 12) in out
     assert "Effective number per param:" in out and "Ratio" in out
+    # the numbers the driver prints, not only the strings: n_eff per parameter and its ratio to the stored samples
+    import re
+    import numpy as np
+    def array_after(label):
+        txt = out[out.index(label) + len(label):]
+        txt = txt[:txt.index("]") + 1]
+        return np.array([float(v) for v in re.findall(r"[-+]?\d*\.?\d+(?:[eE][-+]?\d+)?", txt)])
+    n_eff, ratio = array_after("Effective number per param:"), array_after("Ratio")
+    assert n_eff.shape == ratio.shape == (60,)
+    assert np.all(np.isfinite(n_eff)) and np.all(n_eff > 20) and np.all(n_eff <= 2.5 * 80 * 12)
+    np.testing.assert_allclose(ratio, n_eff / (80 * 12), rtol=1e-6)

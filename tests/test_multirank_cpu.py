@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, x, out_q):
+def _worker(rank, world, port, x, out_q, all_lags=False):
     sys.path.insert(0, os.path.join(ROOT, "understanding-hmc_b200"))
     sys.path.insert(0, ROOT)
     import torch
@@ -46,18 +46,24 @@ def _worker(rank, world, port, x, out_q):
         rows = [np.sum((halves[:, t:] - halves[:, :-t]) ** 2, axis=(0, 1)) for t in range(lag0, lag0 + nl)]
         buf[:nl] = torch.from_numpy(np.stack(rows))
 
+    def all_lags_fn(buf):              # what hmc_diag_variogram_all returns: the numerators of every lag 1..n-1
+        rows = [np.sum((halves[:, t:] - halves[:, :-t]) ** 2, axis=(0, 1)) for t in range(1, n)]
+        buf[:n - 1] = torch.from_numpy(np.stack(rows))
+
     R, ne = U._stats_from_partials(moments_fn, variogram_fn, n, x.shape[2], 2 * (hi - lo), group=None, lag_chunk=8,
-                                   device=torch.device("cpu"))
+                                   device=torch.device("cpu"), all_lags_fn=all_lags_fn if all_lags else None)
     out_q.put((rank, R, ne))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,offset", [(2, 0.0), (2, 1.0e7)])
-def test_sharded_rhat_ess_equals_single_rank(world, offset):
+@pytest.mark.parametrize("world,offset,N,all_lags", [(2, 0.0, 80, False), (2, 1.0e7, 80, False),
+                                                     (2, 0.0, 80, True),      # short chains: one windowed chunk, then the all-lags buffer
+                                                     (2, 0.5, 400, True)])    # long chains (n >= FFT_MIN_N): the all-lags buffer straight away
+def test_sharded_rhat_ess_equals_single_rank(world, offset, N, all_lags):
     import torch.multiprocessing as mp
     rng = np.random.RandomState(0)
-    Nchain, N, D = 6, 80, 4
+    Nchain, D = 6, 4
     x = np.zeros((Nchain, N, D))
     for t in range(1, N):
         x[:, t] = 0.8 * x[:, t - 1] + rng.standard_normal((Nchain, D))
@@ -66,7 +72,7 @@ def test_sharded_rhat_ess_equals_single_rank(world, offset):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, x, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, x, q, all_lags)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]

@@ -18,13 +18,18 @@
 // atomics).  The per-row sums of squares Q[2n][D] are kept by the thread that loads the row.  A small float64 kernel
 // turns (P, Q) into the variogram numerators of all lags.  ~60 kflop per (chain, dimension) instead of 2 n T.
 #include "hmc_common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int kN = 1024;          // transform length
 constexpr int kHalf = 512;        // largest n (samples per split chain)
 constexpr int kThreads = 128;     // 4 warps = 4 dimensions
+constexpr int kZRow = 32 * 33 / 2;// float2 per z row (>= kHalf): the row doubles as a 32 x 33 float transpose plane
 constexpr int kFlush = 32;        // chains between two widenings of the float accumulators
+constexpr int kStepSync = 8;      // chains between two check-ins of the blocks that read the same rows (see `bars`)
+constexpr int kStepLead = 1;      // check-ins a block may be ahead of its slowest sibling (absorbs the jitter between SMs)
+constexpr int kMaxGroups = 64;
 
 // cos(2 pi j / 32), j = 0..8
 __host__ __device__ __forceinline__ constexpr float c32(int j) {
@@ -83,16 +88,27 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Shared memory: twiddles float2 [32][32] | z float2 [4][512] | transpose float [4][32 * 33] | raw float4 [2n] | Qs float4 [2n]
+//
+// `bars` (cooperative launch only, else NULL): the D / 4 blocks of a group read the SAME rows of the same chains, 16 bytes each,
+// and every 64-byte DRAM atom serves four of them -- if they pass by within the L2's reach.  Left alone they drift apart (an
+// SM holds two or three blocks) and the stream is fetched 3.4 times (ncu: 70 GB for 21 GB).  So the blocks of a group check in
+// at a counter every kStepSync chains and wait while they are more than kStepLead check-ins ahead of the slowest sibling; a
+// cooperative launch guarantees that all of them are resident, and a spin limit turns a missing sibling into lost sharing
+// instead of a hang.  Measured: 21.1 GB of DRAM reads for the 21 GB stream.
 __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float* __restrict__ q, long Nchain, int n, int D, long stride_chain,
-                                                                    int groups, double* __restrict__ P, double* __restrict__ Q) {
+                                                                    int groups, double* __restrict__ P, double* __restrict__ Q,
+                                                                    unsigned int* __restrict__ bars) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* tw = reinterpret_cast<float2*>(smraw);                       // [p][lane] = W_1024^(lane * brev5(p))
-    float2* z = tw + 32 * 32;                                            // [4][512]
-    float* tr = reinterpret_cast<float*>(z + 4 * kHalf);                 // [4][32 * 33]
+    float2* z = tw + 32 * 32;                                            // [4][kZRow]: 512 complex inputs; after step 1 the row is the
+                                                                         // imaginary plane of the warp's 32 x 33 transpose tile
+    float* tr = reinterpret_cast<float*>(z + 4 * kZRow);                 // [4][32 * 33]
     float4* raw = reinterpret_cast<float4*>(tr + 4 * 32 * 33);           // [2n]
     float4* Qs = raw + 2 * n;                                            // [2n]
+    __shared__ int sync_lost;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dtile = blockIdx.x / groups, grp = blockIdx.x % groups;
+    if (tid == 0) sync_lost = 0;
     const int d0 = dtile * 4;
     const int rows = 2 * n;
 
@@ -102,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float
         sincospif(-(float)((l * brev5(p)) & (kN - 1)) * (2.0f / kN), &s, &c);
         tw[t] = make_float2(c, s);
     }
-    for (int t = tid; t < 4 * kHalf; t += kThreads) z[t] = make_float2(0.f, 0.f);
+    for (int t = tid; t < 4 * kZRow; t += kThreads) z[t] = make_float2(0.f, 0.f);
     for (int t = tid; t < rows; t += kThreads) Qs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     float acc[32];
@@ -133,9 +149,12 @@ __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float
 
     long chain = grp;
     if (chain < Nchain) issue(chain);
-    int since = 0;
+    int since = 0, step = 0;
+    const unsigned int siblings = gridDim.x / groups;
+    bool in_step = bars != nullptr;
     float* mytr = tr + warp * (32 * 33);
-    const float2* myz = z + warp * kHalf;
+    const float2* myz = z + warp * kZRow;
+    float* myzp = reinterpret_cast<float*>(z + warp * kZRow);
     for (; chain < Nchain; chain += groups) {
         cp_async_wait_all();
         __syncthreads();                                   // rows of this chain have landed; every warp is done with z
@@ -151,10 +170,10 @@ __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float
                 acc4.x = fmaf(y0, y0, acc4.x); acc4.y = fmaf(y1, y1, acc4.y); acc4.z = fmaf(y2, y2, acc4.z); acc4.w = fmaf(y3, y3, acc4.w);
                 Qs[r] = acc4;
                 const int i = second ? r - n : r, comp = second ? 1 : 0;
-                zf[(0 * kHalf + i) * 2 + comp] = y0;
-                zf[(1 * kHalf + i) * 2 + comp] = y1;
-                zf[(2 * kHalf + i) * 2 + comp] = y2;
-                zf[(3 * kHalf + i) * 2 + comp] = y3;
+                zf[(0 * kZRow + i) * 2 + comp] = y0;
+                zf[(1 * kZRow + i) * 2 + comp] = y1;
+                zf[(2 * kZRow + i) * 2 + comp] = y2;
+                zf[(3 * kZRow + i) * 2 + comp] = y3;
             }
         }
         __syncthreads();                                   // z complete, raw free
@@ -163,35 +182,46 @@ __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float
         float re[32], im[32];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            const float2 v = myz[32 * n1 + lane];
-            re[n1] = v.x; im[n1] = v.y;
+            const float2 v = (32 * n1 + lane < n) ? myz[32 * n1 + lane] : make_float2(0.f, 0.f);   // (beyond n the row holds the previous
+            re[n1] = v.x; im[n1] = v.y;                                                             //  chain's transpose plane)
         }
 #pragma unroll
         for (int n1 = 16; n1 < 32; ++n1) { re[n1] = 0.f; im[n1] = 0.f; }
         fft32<true>(re, im);
 #pragma unroll
-        for (int p = 0; p < 32; ++p) {                     // twiddle, then the real plane of the transpose
-            const float2 w = tw[p * 32 + lane];
+        for (int p = 0; p < 32; ++p) {                     // twiddle (all table loads ahead of the transpose's stores: the compiler
+            const float2 w = tw[p * 32 + lane];            //  cannot tell that the two shared arrays do not alias)
             const float r2 = fmaf(re[p], w.x, -im[p] * w.y);
             im[p] = fmaf(re[p], w.y, im[p] * w.x);
             re[p] = r2;
-            mytr[brev5(p) * 33 + lane] = r2;
         }
+        __syncwarp();                                      // every lane has read its part of z: the row doubles as the second plane
+#pragma unroll
+        for (int p = 0; p < 32; ++p) { mytr[brev5(p) * 33 + lane] = re[p]; myzp[brev5(p) * 33 + lane] = im[p]; }
         __syncwarp();
 #pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) re[n2] = mytr[lane * 33 + n2];
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < 32; ++p) mytr[brev5(p) * 33 + lane] = im[p];
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) im[n2] = mytr[lane * 33 + n2];
+        for (int n2 = 0; n2 < 32; ++n2) { re[n2] = mytr[lane * 33 + n2]; im[n2] = myzp[lane * 33 + n2]; }
         __syncwarp();
         fft32<false>(re, im);
 #pragma unroll
         for (int p = 0; p < 32; ++p) acc[p] = fmaf(re[p], re[p], fmaf(im[p], im[p], acc[p]));
 
         if (++since == kFlush) { flush(); since = 0; }
+        if (in_step && (++step % kStepSync) == 0) {
+            __syncthreads();
+            if (tid == 0) {
+                const int behind = step / kStepSync - kStepLead;          // everybody must have finished this check-in
+                const unsigned int target = behind > 0 ? (unsigned int)behind * siblings : 0u;
+                atomicAdd(bars + grp, 1u);
+                const long long t0 = clock64();
+                while (*reinterpret_cast<volatile unsigned int*>(bars + grp) < target) {
+                    __nanosleep(100);
+                    if (clock64() - t0 > 200000000ll) { *reinterpret_cast<volatile int*>(&sync_lost) = 1; break; }
+                }
+            }
+            __syncthreads();
+            if (*reinterpret_cast<volatile int*>(&sync_lost)) in_step = false;      // (same decision in every warp: read after the barrier)
+        }
     }
     if (since) flush();
 }
@@ -294,7 +324,7 @@ int main() {
     } while (0)
 
 extern "C" int64_t hmc_diag_variogram_all_workspace_bytes(int64_t n, int32_t D) {
-    return (int64_t)sizeof(double) * ((int64_t)D * kN + 2 * n * (int64_t)D);
+    return (int64_t)sizeof(double) * ((int64_t)D * kN + 2 * n * (int64_t)D + kMaxGroups);
 }
 
 extern "C" int hmc_diag_variogram_all(int32_t dtype, const void* q, int64_t Nchain, int64_t n, int32_t D, int64_t stride_chain,
@@ -319,9 +349,27 @@ extern "C" int hmc_diag_variogram_all(int32_t dtype, const void* q, int64_t Ncha
     int groups = (3 * sms) / dtiles;                     // three resident blocks per SM, one wave
     if (groups < 1) groups = 1;
     if (groups > Nchain) groups = (int)Nchain;
-    const size_t smem = sizeof(float2) * (32 * 32 + 4 * kHalf) + sizeof(float) * 4 * 32 * 33 + sizeof(float4) * 4 * (size_t)n;
+    const size_t smem = sizeof(float2) * (32 * 32 + 4 * kZRow) + sizeof(float) * 4 * 32 * 33 + sizeof(float4) * 4 * (size_t)n;
     HMC_CUDA_CHECK(cudaFuncSetAttribute(diag_fft_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    diag_fft_power_kernel<<<dtiles * groups, kThreads, smem, stream>>>((const float*)q, Nchain, (int)n, D, stride_chain, groups, P, Q);
+    if (groups > kMaxGroups) groups = kMaxGroups;
+    // cooperative launch when every block fits at once (then the sibling blocks may wait for each other); plain launch otherwise
+    unsigned int* bars = reinterpret_cast<unsigned int*>(Q + 2 * (size_t)n * D);
+    int coop = 0, per_sm = 0;
+    HMC_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    HMC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, diag_fft_power_kernel, kThreads, smem));
+    const float* qf = (const float*)q;
+    long nch = Nchain;
+    int ni = (int)n, gr = groups;
+    bool launched = false;
+    if (coop && (long)per_sm * sms >= (long)dtiles * groups && dtiles > 1 && getenv("HMC_B200_DIAG_FFT_FREE") == nullptr) {
+        void* kargs[] = {&qf, &nch, &ni, &D, &stride_chain, &gr, &P, &Q, &bars};
+        launched = cudaLaunchCooperativeKernel((const void*)diag_fft_power_kernel, dim3(dtiles * groups), dim3(kThreads), kargs, smem, stream) == cudaSuccess;
+        if (!launched) (void)cudaGetLastError();
+    }
+    if (!launched) {
+        unsigned int* none = nullptr;
+        diag_fft_power_kernel<<<dtiles * groups, kThreads, smem, stream>>>(qf, nch, ni, D, stride_chain, gr, P, Q, none);
+    }
     diag_fft_finish_kernel<<<D, kHalf, 0, stream>>>(P, Q, (int)n, D, nlags, out_nlags_x_D);
     HMC_CUDA_CHECK(cudaGetLastError());
     return HMC_OK;
