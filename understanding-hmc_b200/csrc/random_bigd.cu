@@ -35,8 +35,11 @@ namespace {
 
 constexpr int BM = 128;            // chains per tile (UMMA M)
 constexpr int BN_MAX = 256;        // dimensions per tile (UMMA N; fp32 accumulator columns): 256 for the two-part split, 128 for the three-part one (shared memory)
-constexpr int BK = 64;             // K per stage: 64 16-bit elements = one 128-byte swizzle row
-constexpr int STAGES = 2;
+// K per stage is a template parameter BK in {64, 32, 16} (one swizzle row of 128 / 64 / 32 bytes) with 128 / BK stages: the bytes
+// of operand memory are the same, the pipeline is finer -- a stage can only be refilled after its MMAs are done, so with two
+// 96 KB stages one load is in flight while the other stage is consumed and the tensor pipe waits for most of a load's latency.
+constexpr int kStageK = 128;       // stages x BK
+constexpr int kMaxCluster = 4;     // largest cluster of row blocks (the chain count is padded to whole clusters)
 constexpr int EB = 8;              // epilogue column block
 constexpr int NEPI = 8;            // epilogue warps: two per TMEM lane quarter, alternating column blocks
 constexpr int NTHREADS = 64 + 32 * NEPI;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
@@ -63,17 +66,35 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same load delivered to the same shared-memory offset (data and mbarrier signal) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+// MMA completion signalled on the mbarrier at this offset in every CTA of `mask` (a stage is shared by the cluster's producers)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// K-major operand tile [rows][64 x 16 bit] written by TMA with the 128-byte swizzle: 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+// K-major operand tile [rows][BK x 16 bit] written by TMA with the swizzle of its row length (128 / 64 / 32 bytes): 8-row groups
+// 8 x row bytes apart; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr) {
+    constexpr uint32_t row_bytes = BK * 2;
+    constexpr uint64_t layout = (BK == 64) ? 2 : (BK == 32 ? 4 : 6);
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);
     d |= (uint64_t)1 << 16;                              // leading byte offset: unused for swizzled K-major (set to 1)
-    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;        // stride byte offset: 8 rows x 128 bytes
+    d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3fff) << 32;   // stride byte offset: 8 rows
     d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+    d |= layout << 61;
     return d;
 }
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -130,10 +151,14 @@ struct BigdWs {                      // workspace carved by the host (all device
     int Ncp, NT, npart;
 };
 
-template <int NPART, int BN>
+// CL = CTAs per cluster (launch attribute): the CL row blocks of a cluster work on the SAME column block at the same time, each
+// CTA loads 1 / CL of the B tile and multicasts it to the others -- the L2 -> SM traffic of a tile drops from A + B to A + B / CL
+// (the kernel was bound by exactly that traffic: 4.0 TB/s of L2 reads at 23 % tensor-pipe activity with CL = 1).
+template <int NPART, int BN, int CL, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                               BigdWs w, int Nchain, int D, const float* __restrict__ dtv) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int STAGES = kStageK / BK;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;                 // one part of one stage
     constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
     unsigned char* stage_base = smem;
@@ -147,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }   // a stage is refilled by all CL producers
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -157,29 +182,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();              // barriers of every CTA initialised before anybody signals them
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
     const int NT = w.NT, KB = D / BK;
-    const int ntiles = (w.Ncp / BM) * NT;
+    const int ntiles = (w.Ncp / (BM * CL)) * NT;            // work items of a cluster: (CL row blocks, one column block)
     const size_t part_rows_a = (size_t)w.Ncp, part_rows_b = (size_t)D;
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    // the same decision in every CTA of the cluster (their loops must stay in step): skip a work item only if all its row blocks are idle
+    auto item_active = [&](int mtc) { int any = 0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) any |= w.tile_active[mtc * CL + r];
+        return any != 0; };
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t n = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const int mt = t / NT, nt = t % NT;
-                if (!w.tile_active[mt]) continue;
+            for (int t = cid; t < ntiles; t += ncl) {
+                const int mtc = t / NT, nt = t % NT;
+                if (!item_active(mtc)) continue;
+                const int mt = mtc * CL + crank;
                 for (int kb = 0; kb < KB; ++kb, ++n) {
                     const int s = n % STAGES;
-                    mbar_wait(empty + s, ((n / STAGES) & 1) ^ 1);
+                    mbar_wait(empty + s, ((n / STAGES) & 1) ^ 1);           // released by the MMA warps of all CL CTAs
                     unsigned char* sb = stage_base + s * STAGE_BYTES;
-                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    mbar_expect_tx(full + s, STAGE_BYTES);                   // my A parts + the whole B tile (1 / CL of it from each CTA)
 #pragma unroll
                     for (int pt = 0; pt < NPART; ++pt) {
                         tma_load_2d(sb + pt * A_BYTES, &mapA, kb * BK, (int)(pt * part_rows_a) + mt * BM, full + s);
-                        tma_load_2d(sb + NPART * A_BYTES + pt * B_BYTES, &mapB, kb * BK, (int)(pt * part_rows_b) + nt * BN, full + s);
+                        if constexpr (CL == 1)
+                            tma_load_2d(sb + NPART * A_BYTES + pt * B_BYTES, &mapB, kb * BK, (int)(pt * part_rows_b) + nt * BN, full + s);
+                        else
+                            tma_load_2d_mc(sb + NPART * A_BYTES + pt * B_BYTES + crank * (B_BYTES / CL), &mapB, kb * BK,
+                                           (int)(pt * part_rows_b) + nt * BN + crank * (BN / CL), full + s, cmask);
                     }
+                }
+            }
+            if constexpr (CL > 1) {                                          // every release aimed at this CTA has arrived before it may exit
+                for (uint32_t k = 0; k < STAGES && k < n; ++k) {
+                    const uint32_t m = n - 1 - k;
+                    mbar_wait(empty + (m % STAGES), (m / STAGES) & 1);
                 }
             }
         }
@@ -189,9 +234,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             constexpr uint32_t fmt = (NPART == 2) ? 0u : 1u;       // 0 = f16, 1 = bf16
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             uint32_t n = 0, nt_done = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const int mt = t / NT;
-                if (!w.tile_active[mt]) continue;
+            for (int t = cid; t < ntiles; t += ncl) {
+                if (!item_active(t / NT)) continue;
                 const int as = nt_done & 1;
                 mbar_wait(tempty + as, ((nt_done >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -210,12 +254,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                         const int pa = (NPART == 2) ? pa2[pr % 3] : pa3[pr], pb = (NPART == 2) ? pb2[pr % 3] : pb3[pr];
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t ad = make_desc_sw128(sa + pa * A_BYTES + k * 32);
-                            const uint64_t bd = make_desc_sw128(sbb + pb * B_BYTES + k * 32);
+                            const uint64_t ad = make_desc_sw<BK>(sa + pa * A_BYTES + k * 32);
+                            const uint64_t bd = make_desc_sw<BK>(sbb + pb * B_BYTES + k * 32);
                             umma_ss(tacc, ad, bd, idesc, (kb | pr | k) ? 1u : 0u);
                         }
                     }
-                    umma_commit(empty + s);                   // frees the stage when these MMAs are done
+                    if constexpr (CL == 1) umma_commit(empty + s);           // frees the stage when these MMAs are done
+                    else umma_commit_mc(empty + s, cmask);                    // ... in every CTA of the cluster (all of them refill it)
                 }
                 umma_commit(tfull + as);                      // accumulator complete
                 ++nt_done;
@@ -231,9 +276,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
         uint32_t* Hs = reinterpret_cast<uint32_t*>(Xs + 32 * (EB + 1));            // [NPART][32][EB / 2 + 1]
         uint32_t nt_done = 0;
         const int sub = lane >> 3, col = lane & 7;              // global <-> shared: 8 lanes per row segment, 4 row segments per instruction
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const int mt = t / NT, nt = t % NT;
-            if (!w.tile_active[mt]) continue;
+        for (int t = cid; t < ntiles; t += ncl) {
+            const int mtc = t / NT, nt = t % NT;
+            if (!item_active(mtc)) continue;
+            const int mt = mtc * CL + crank;
             const int as = nt_done & 1;
             const long row0 = (long)mt * BM + quarter * 32;          // first chain of this warp
             const long chain = row0 + lane;
@@ -260,6 +306,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                 auto block = [&](float (&v)[16], int b) {
                     const int cb = half + 2 * b;
                     const int c0 = nt * BN + cb * EB;
+                    // (the step sizes of the block's columns are requested first: left inside the arithmetic loop each of them was a
+                    //  global-load latency in front of the first use -- 32 % of the kernel's stall samples)
+                    const float4 dta = __ldg(reinterpret_cast<const float4*>(dtv + c0)), dtb = __ldg(reinterpret_cast<const float4*>(dtv + c0 + 4));
+                    const float dts[EB] = {dta.x, dta.y, dta.z, dta.w, dtb.x, dtb.y, dtb.z, dtb.w};
 #pragma unroll
                     for (int i = 0; i < 16; ++i) sdst[2 * i * (EB + 1)] = v[i];
                     __syncwarp();
@@ -273,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
 #pragma unroll
                     for (int j = 0; j < EB; ++j) {
                         const float g = __uint_as_float(gv[j]);
-                        const float dtj = __ldg(dtv + c0 + j);
+                        const float dtj = dts[j];
                         const float xo = Xs[lane * (EB + 1) + j];
                         hv = fmaf(xo, g, hv);
                         const float pn = fmaf(g, kw * dtj, Ps[lane * (EB + 1) + j]);       // samplers.py:835, 837
@@ -328,6 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    if constexpr (CL > 1) cluster_sync_all();              // nobody leaves while a peer may still write into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -566,16 +617,17 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D map over a [rows][D] matrix of 16-bit elements, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, bool f16, void* base, uint64_t rows, uint64_t D, uint32_t box_rows) {
+// 2-D map over a [rows][D] matrix of 16-bit elements, box = bk elements (128 / 64 / 32 bytes) x box_rows, swizzle of that width
+int make_map(CUtensorMap* map, bool f16, void* base, uint64_t rows, uint64_t D, uint32_t box_rows, int bk) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { hmc_set_error("cuTensorMapEncodeTiled is not available from the driver"); return HMC_E_CUDA; }
     const cuuint64_t dims[2] = {D, rows};
     const cuuint64_t strides[1] = {D * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
+    const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { hmc_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return HMC_E_CUDA; }
     return HMC_OK;
@@ -585,7 +637,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // carve the workspace; returns the bytes needed (ws may be NULL to only size it)
 size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn) {
-    const long Ncp = (Nchain + BM - 1) / BM * BM;
+    const long Ncp = (Nchain + BM * kMaxCluster - 1) / (BM * kMaxCluster) * (BM * kMaxCluster);   // whole clusters of row blocks
     const int NT = D / bn;
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char* p = ws ? ws + off : nullptr; off = align_up(off + bytes, 1024); return p; };
@@ -607,11 +659,11 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
 
 template <int NPART, int BN>
 constexpr size_t gemm_smem_bytes() {
-    return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + NEPI * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 16 * 8 + 64;
+    return (size_t)NPART * (BM * kStageK * 2 + BN * kStageK * 2) + NEPI * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 32 * 8 + 64;
 }
 static_assert(gemm_smem_bytes<2, 256>() <= 232448 && gemm_smem_bytes<3, 128>() <= 232448, "shared memory of the large-D GEMM exceeds 227 KB");
 
-template <int NPART, int BN>
+template <int NPART, int BN, int CL, int BK>
 int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     const int D = a.target.D;
     BigdWs w;
@@ -640,15 +692,35 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     w.binv = 1.f / scale;
     bigd_split_matrix<NPART><<<sms * 8, 256, 0, stream>>>((const float*)a.target.Ft, D, a.target.D_pad, scale, w.bp);
     CUtensorMap mapA, mapB;
-    if (int rc = make_map(&mapA, NPART == 2, w.xp, (uint64_t)NPART * w.Ncp, D, BM)) return rc;
-    if (int rc = make_map(&mapB, NPART == 2, w.bp, (uint64_t)NPART * D, D, BN)) return rc;
+    if (int rc = make_map(&mapA, NPART == 2, w.xp, (uint64_t)NPART * w.Ncp, D, BM, BK)) return rc;
+    if (int rc = make_map(&mapB, NPART == 2, w.bp, (uint64_t)NPART * D, D, BN / CL, BK)) return rc;      // each CTA of a cluster loads 1 / CL of a B tile
     bigd_init<NPART><<<(w.Ncp + 3) / 4, 128, 0, stream>>>(a, w);
     const int ntile_rows = w.Ncp / BM;
     HMC_CUDA_CHECK(cudaMemsetAsync(w.tile_active, 0xff, (size_t)ntile_rows * 4, stream));
     const size_t smem = gemm_smem_bytes<NPART, BN>();
-    HMC_CUDA_CHECK(cudaFuncSetAttribute(bigd_gemm_step<NPART, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ntiles = ntile_rows * w.NT;
-    const int grid = ntiles < sms ? ntiles : sms;
+    auto kern = bigd_gemm_step<NPART, BN, CL, BK>;
+    HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (ntile_rows / CL) * w.NT;                 // work items of a cluster
+    // persistent clusters: as many as are resident at once (a GPC holds whole clusters only), never more than there is work
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(sms / CL * CL); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = sms / CL;
+    if (CL > 1) {
+        int nc = 0;
+        HMC_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+        if (nc < 1) { hmc_set_error("large-D kernel: no cluster of %d CTAs fits on this device", CL); return HMC_E_CUDA; }
+        if (nc < max_clusters) max_clusters = nc;
+    }
+    const int nclusters = ntiles < max_clusters ? ntiles : max_clusters;
+    const int grid = nclusters * CL;
+    cfg.gridDim = dim3(grid);
+    const float* dtv = (const float*)a.target.dt;
+    const int Nch = a.Nchain;
+    auto launch_gemm = [&]() { return cudaLaunchKernelEx(&cfg, kern, mapA, mapB, w, Nch, D, dtv); };
     int* running_h = nullptr;
     HMC_CUDA_CHECK(cudaMallocHost(&running_h, 4));
     const long max_pass = (long)(a.iter_end - a.iter_begin) * (a.L_high + 1) + 8;
@@ -661,7 +733,7 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     for (long pass = 0; pass < max_pass; ++pass) {
         if (timing && pass >= 4 && pass < 12) {
             cudaEventRecord(ev[0], stream);
-            bigd_gemm_step<NPART, BN><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, w, a.Nchain, D, (const float*)a.target.dt);
+            launch_gemm();
             cudaEventRecord(ev[1], stream);
             cudaMemsetAsync(w.counters + 2, 0, 4, stream);
             bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
@@ -670,11 +742,11 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
             cudaEventRecord(ev[3], stream);
             cudaEventSynchronize(ev[3]);
             for (int i = 0; i < 3; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); tsum[i] += ms; }
-            if (pass == 11) fprintf(stderr, "[bigd timing] NPART=%d BN=%d chains=%d D=%d: gemm_step %.3f ms, events %.3f ms, trajectory_end %.3f ms per pass (%d tiles on %d CTAs)\n",
-                                    NPART, BN, a.Nchain, D, tsum[0] / 8, tsum[1] / 8, tsum[2] / 8, ntiles, grid);
+            if (pass == 11) fprintf(stderr, "[bigd timing] NPART=%d BN=%d BK=%d cluster=%d chains=%d D=%d: gemm_step %.3f ms, events %.3f ms, trajectory_end %.3f ms per pass (%d work items on %d CTAs)\n",
+                                    NPART, BN, BK, CL, a.Nchain, D, tsum[0] / 8, tsum[1] / 8, tsum[2] / 8, ntiles, grid);
             continue;
         }
-        bigd_gemm_step<NPART, BN><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, w, a.Nchain, D, (const float*)a.target.dt);
+        if (launch_gemm() != cudaSuccess) { rc = HMC_E_CUDA; break; }
         cudaMemsetAsync(w.counters + 2, 0, 4, stream);
         bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
         bigd_trajectory_end<NPART><<<sms * 2, 256, 0, stream>>>(a, w, (int)pass);
@@ -711,5 +783,17 @@ size_t hmc_random_bigd_workspace(const hmc_random_args& a) {
 int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     bool fp16 = (a.flags & HMC_FLAG_TC_FP16X2) != 0;
     if (const char* e = getenv("HMC_B200_TC_PREC")) fp16 = (e[0] == 'f');
-    return fp16 ? run_bigd<2, 256>(a, stream) : run_bigd<3, 128>(a, stream);
+    // Measured alternatives, kept selectable (HMC_B200_BIGD_CLUSTER=2: clusters of two row blocks with the B tile multicast;
+    // HMC_B200_BIGD_BK=32: four 48 KB stages instead of two 96 KB ones).  Neither moves the pass time (1.22-1.28 ms at 131,072
+    // chains): the L2 already merges the concurrent unicast reads of a B tile, and the kernel is bound by its epilogue, not by
+    // the operand pipeline.  Default: one CTA per tile, two stages of K = 64.
+    int cl = 1, bk = 64;
+    if (const char* e = getenv("HMC_B200_BIGD_CLUSTER")) cl = atoi(e);
+    if (const char* e = getenv("HMC_B200_BIGD_BK")) bk = atoi(e);
+    if (fp16) {
+        if (cl == 2) return run_bigd<2, 256, 2, 64>(a, stream);
+        return bk == 32 ? run_bigd<2, 256, 1, 32>(a, stream) : run_bigd<2, 256, 1, 64>(a, stream);
+    }
+    if (cl == 2) return run_bigd<3, 128, 2, 64>(a, stream);
+    return bk == 32 ? run_bigd<3, 128, 1, 32>(a, stream) : run_bigd<3, 128, 1, 64>(a, stream);
 }
