@@ -5,13 +5,14 @@
 // Follows HMC_sampler.gen_sample_random + leap_frog (/root/reference/samplers.py:387-491, 831-839).
 //
 // One PASS = one gradient evaluation for every chain (per-step GEMM with the leapfrog update fused in):
-//   bigd_gemm_step   persistent CTAs over (128 chains x 256 dimensions) tiles, K = D.  Warp 0 issues the TMA loads
-//                    (cp.async.bulk.tensor, 128-byte swizzle, 2 stages of K = 64), warp 1 issues the tcgen05.mma
-//                    (cta_group::1, kind::f16, M = 128, N = 256, fp32 accumulators double-buffered in the 512 TMEM columns),
-//                    warps 2..9 are the epilogue: tcgen05.ld of the tile, per-chain kick / drift weights by trajectory
-//                    phase (first point: half kick + drift, interior: full kick + drift, last: half kick), momentum and
-//                    position updated in place, the NEXT pass's A operand (the split position) written, partial sums of
-//                    q.g and p.p per (chain, column tile) for the energies.
+//   bigd_gemm_step   persistent CTAs (clusters of two row blocks) over (128 chains x 256 dimensions) tiles, K = D.  Warp 0 issues
+//                    the TMA loads (cp.async.bulk.tensor, 64-byte swizzle, 3 stages of K = 32; the B tile multicast to the
+//                    cluster), warp 1 issues the tcgen05.mma (cta_group::1, kind::f16, M = 128, N = 256, fp32 accumulators
+//                    double-buffered in the 512 TMEM columns), warps 2..5 are the epilogue: tcgen05.ld of a 16-column chunk, the
+//                    chunk's momentum and position rows brought in by TMA, per-chain kick / drift weights by trajectory phase
+//                    (first point: half kick + drift, interior: full kick + drift, last: half kick), momentum and position
+//                    updated in shared memory and stored by TMA, the NEXT pass's A operand (the split position) stored by TMA
+//                    into the other operand buffer, partial sums of q.g and p.p per (chain, column tile) for the energies.
 //                    FP32-grade product from a two-part fp16 split (x = h1 + h2, F 2^s = f1 + f2; products (1,2) (2,1) (1,1)
 //                    per K step) -- or the three-part bf16 split with six products (flags bit 1 clear).
 //   bigd_events      one thread per chain: trajectory bookkeeping (energies, Metropolis accept on the Philox uniform, step
@@ -40,9 +41,12 @@ constexpr int BN_MAX = 256;        // dimensions per tile (UMMA N; fp32 accumula
 // 96 KB stages one load is in flight while the other stage is consumed and the tensor pipe waits for most of a load's latency.
 constexpr int kStageK = 128;       // stages x BK
 constexpr int kMaxCluster = 4;     // largest cluster of row blocks (the chain count is padded to whole clusters)
-constexpr int EB = 8;              // epilogue column block
-constexpr int NEPI = 8;            // epilogue warps: two per TMEM lane quarter, alternating column blocks
-constexpr int NTHREADS = 64 + 32 * NEPI;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int CW = 16;             // epilogue chunk: 16 columns of a warp's 32 chains
+constexpr int NEPI = 4;            // epilogue warps: one per TMEM lane quarter
+constexpr int NBUF = 3;            // chunk buffers per epilogue warp (one in arithmetic, one being stored, one loading)
+constexpr int NTHREADS = 64 + 32 * NEPI;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int EPB_PX = 32 * CW * 4;           // one float32 array of a chunk: 32 rows x 64 bytes, SWIZZLE_64B
+constexpr int EPB_PART = 32 * CW * 2;         // one 16-bit part of a chunk: 32 rows x 32 bytes, SWIZZLE_32B
 enum : int { MD_IDLE = 0, MD_FIRST = 1, MD_MID = 2, MD_LAST = 3, MD_PENDING = 4 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +84,13 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -128,7 +139,9 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t (&h)[3])
 }
 
 struct BigdWs {                      // workspace carved by the host (all device pointers)
-    uint16_t* xp;                    // [NPART][Ncp][D]  split position = A operand of the next pass
+    uint16_t* xp;                    // [2][NPART][Ncp][D]  split position = A operand: pass n reads buffer n & 1 and writes the other one
+                                     // (the column tiles of a row block read ALL its columns while one of them already writes its own)
+    int wr;                          // buffer the parts of the next pass go to (set per launch)
     uint16_t* bp;                    // [NPART][D][D]    split force matrix (x 2^s for the fp16 split) = B operand
     float* x;                        // [Ncp][D] shifted position q - mu
     float* x0;                       // [Ncp][D] position at the start of the running trajectory
@@ -154,26 +167,34 @@ struct BigdWs {                      // workspace carved by the host (all device
 // CL = CTAs per cluster (launch attribute): the CL row blocks of a cluster work on the SAME column block at the same time, each
 // CTA loads 1 / CL of the B tile and multicasts it to the others -- the L2 -> SM traffic of a tile drops from A + B to A + B / CL
 // (the kernel was bound by exactly that traffic: 4.0 TB/s of L2 reads at 23 % tensor-pipe activity with CL = 1).
-template <int NPART, int BN, int CL, int BK>
+// The epilogue moves its rows by TMA as well: mapP / mapX are the momentum and position arrays [Ncp][D] float32 (box 16 columns x
+// 32 rows, 64-byte swizzle; loaded and stored through the same map), mapS the 16-bit parts of the NEXT pass's A operand (box 16 x 32,
+// 32-byte swizzle; mapA reads the parts of THIS pass: the two live in different buffers, alternating by pass, because the row blocks
+// of a chain tile are read in full by every column tile while one of them already writes its columns).
+template <int NPART, int BN, int CL, int BK, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                              const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX,
+                                                              const __grid_constant__ CUtensorMap mapS,
                                                               BigdWs w, int Nchain, int D, const float* __restrict__ dtv) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int STAGES = kStageK / BK;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;                 // one part of one stage
     constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
     unsigned char* stage_base = smem;
-    unsigned char* epi = smem + STAGES * STAGE_BYTES;                           // epilogue staging, per warp
-    constexpr int EPI_WARP_BYTES = 2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4;
+    unsigned char* epi = smem + STAGES * STAGE_BYTES;                           // epilogue chunk buffers, per warp
+    constexpr int EPI_BUF_BYTES = 2 * EPB_PX + NPART * EPB_PART;               // momentum | position | parts of one chunk
+    constexpr int EPI_WARP_BYTES = NBUF * EPI_BUF_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi + NEPI * EPI_WARP_BYTES);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + STAGES;       // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;   // [2]
     uint64_t* tempty = bars + 2 * STAGES + 2;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* efull = bars + 2 * STAGES + 4;    // [NEPI][NBUF] chunk loaded
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NEPI * NBUF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }   // a stage is refilled by all CL producers
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, NEPI); }
+        for (int s = 0; s < NEPI * NBUF; ++s) mbar_init(efull + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 1) {
@@ -267,15 +288,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 = chains of the tile; the two warps of a lane quarter take
-        //       alternating 8-column blocks.  Rows travel through a padded shared-memory tile so that global accesses are row
-        //       segments (coalesced) while the arithmetic is one thread per chain (the layout tcgen05.ld delivers). =========
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
-        float* Ps = reinterpret_cast<float*>(epi + (warp - 2) * EPI_WARP_BYTES);     // [32][EB + 1]
-        float* Xs = Ps + 32 * (EB + 1) + 16;                                        // [32][EB + 1] (16 words on: other banks than Ps)
-        uint32_t* Hs = reinterpret_cast<uint32_t*>(Xs + 32 * (EB + 1));            // [NPART][32][EB / 2 + 1]
+        // ===== epilogue warps: TMEM lanes 32 (warp % 4) .. + 31 = 32 chains of the tile, one thread per chain (the layout
+        //       tcgen05.ld delivers).  The momentum and position rows of a 16-column chunk arrive by TMA (64-byte swizzle: a thread's
+        //       16-byte pieces of its row fall on distinct banks), are updated in place, go back by TMA together with the split
+        //       position; NBUF chunk buffers per warp, the load of chunk g + 2 is issued when the store of chunk g - 1 has left its
+        //       buffer.  (The first version moved every element through registers -> padded tile -> registers twice: ~150 LSU
+        //       instructions per 256 elements, and ran at 26 % tensor-pipe activity whatever the operand pipeline did.) ==========
+        const int quarter = warp & 3, ew = warp - 2;
+        unsigned char* ebase = epi + ew * EPI_WARP_BYTES;
+        uint64_t* ef = efull + ew * NBUF;
+        constexpr int NCH = BN / CW;                        // chunks of a tile
+        // a tile is LIVE for this warp when one of its 32 chains takes part in the pass; only live tiles enter the chunk stream
+        auto tile_md = [&](int tt) { const long ch = (long)((tt / NT) * CL + crank) * BM + quarter * 32 + lane;
+                                     return (ch < Nchain) ? w.mode[ch] : (int)MD_IDLE; };
+        auto is_live = [&](int md) { return __any_sync(HMC_FULL_MASK, md == MD_FIRST || md == MD_MID || md == MD_LAST) != 0; };
+        auto next_live = [&](int tt) { for (tt += ncl; tt < ntiles; tt += ncl) if (item_active(tt / NT) && is_live(tile_md(tt))) break; return tt; };
+        auto issue_chunk = [&](int tt, int c, uint32_t g) {      // lane 0: chunk c of tile tt is the g-th chunk of this warp's stream
+            const int buf = g % NBUF;
+            unsigned char* bp = ebase + buf * EPI_BUF_BYTES;
+            const int col0 = (tt % NT) * BN + c * CW, row0 = ((tt / NT) * CL + crank) * BM + quarter * 32;
+            mbar_expect_tx(ef + buf, 2 * EPB_PX);
+            tma_load_2d(bp, &mapP, col0, row0, ef + buf);
+            tma_load_2d(bp + EPB_PX, &mapX, col0, row0, ef + buf);
+        };
+        // prefetch cursor: (pf_t, pf_c) = the next chunk to request, pf_g its number in the stream
+        int pf_t = cid - ncl;
+        pf_t = next_live(pf_t);
+        int pf_c = 0;
+        uint32_t pf_g = 0, g = 0;
+        auto prefetch_one = [&]() {
+            if (pf_t >= ntiles) return;
+            if (lane == 0) issue_chunk(pf_t, pf_c, pf_g);
+            ++pf_g;
+            if (++pf_c == NCH) { pf_c = 0; pf_t = next_live(pf_t); }
+        };
+        prefetch_one();
+        prefetch_one();
         uint32_t nt_done = 0;
-        const int sub = lane >> 3, col = lane & 7;              // global <-> shared: 8 lanes per row segment, 4 row segments per instruction
+        const int swz = (lane >> 1) & 3;                        // 64-byte swizzle of my row: 16-byte piece c sits at piece c ^ swz
+        const int swz2 = (lane >> 2) & 1;                       // 32-byte swizzle of my row
         for (int t = cid; t < ntiles; t += ncl) {
             const int mtc = t / NT, nt = t % NT;
             if (!item_active(mtc)) continue;
@@ -283,97 +334,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             const int as = nt_done & 1;
             const long row0 = (long)mt * BM + quarter * 32;          // first chain of this warp
             const long chain = row0 + lane;
-            const int md = (chain < Nchain) ? w.mode[chain] : MD_IDLE;
+            const int md = tile_md(t);
             const float kw = (md == MD_MID) ? -w.binv : ((md == MD_FIRST || md == MD_LAST) ? -0.5f * w.binv : 0.f);
             const float dw = (md == MD_FIRST || md == MD_MID) ? 1.f : 0.f;
-            const bool live = __any_sync(HMC_FULL_MASK, md == MD_FIRST || md == MD_MID || md == MD_LAST);
+            const bool live = is_live(md);
             mbar_wait(tfull + as, (nt_done >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             float hv = 0.f, hk = 0.f;
             if (live) {
-                // The row segments of a column block are requested TWO blocks ahead (the epilogue was bound by the latency of these
-                // loads: ncu long-scoreboard 8.3 per issue, tensor pipe 26 %): registers va / vb hold the blocks in flight.
-                constexpr int NB = BN / EB / 2;                  // column blocks of this warp in a tile
-                const float* gsrc = ((sub & 1) ? w.x : w.p) + (size_t)nt * BN + col + (size_t)(row0 + (sub >> 1)) * D;
-                float* gdst = ((sub & 1) ? w.x : w.p) + (size_t)nt * BN + col + (size_t)(row0 + (sub >> 1)) * D;
-                float* sdst = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
-                float va[16], vb[16];
-                auto request = [&](float (&v)[16], int b) {
-                    const float* src = gsrc + (half + 2 * b) * EB;
+                for (int c = 0; c < NCH; ++c, ++g) {
+                    const int buf = g % NBUF;
+                    unsigned char* bp = ebase + buf * EPI_BUF_BYTES;
+                    const int c0 = nt * BN + c * CW;
+                    float dts[CW];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __ldcs(src + (size_t)(2 * i) * D);
-                };
-                auto block = [&](float (&v)[16], int b) {
-                    const int cb = half + 2 * b;
-                    const int c0 = nt * BN + cb * EB;
-                    // (the step sizes of the block's columns are requested first: left inside the arithmetic loop each of them was a
-                    //  global-load latency in front of the first use -- 32 % of the kernel's stall samples)
-                    const float4 dta = __ldg(reinterpret_cast<const float4*>(dtv + c0)), dtb = __ldg(reinterpret_cast<const float4*>(dtv + c0 + 4));
-                    const float dts[EB] = {dta.x, dta.y, dta.z, dta.w, dtb.x, dtb.y, dtb.z, dtb.w};
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sdst[2 * i * (EB + 1)] = v[i];
-                    __syncwarp();
-                    if (b + 2 < NB) request(v, b + 2);          // this buffer's next block, in flight during the arithmetic below
-                    uint32_t gv[8];
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                 : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7])
-                                 : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + cb * EB)));
+                    for (int i = 0; i < CW / 4; ++i) {
+                        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dtv + c0) + i);
+                        dts[4 * i] = d4.x; dts[4 * i + 1] = d4.y; dts[4 * i + 2] = d4.z; dts[4 * i + 3] = d4.w;
+                    }
+                    uint32_t gv[16];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(gv[0]), "=r"(gv[1]), "=r"(gv[2]), "=r"(gv[3]), "=r"(gv[4]), "=r"(gv[5]), "=r"(gv[6]), "=r"(gv[7]),
+                                   "=r"(gv[8]), "=r"(gv[9]), "=r"(gv[10]), "=r"(gv[11]), "=r"(gv[12]), "=r"(gv[13]), "=r"(gv[14]), "=r"(gv[15])
+                                 : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c * CW)));
+                    mbar_wait(ef + buf, (g / NBUF) & 1);                 // momentum and position rows of the chunk have landed
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float xn[EB];
+                    float4* prow = reinterpret_cast<float4*>(bp + lane * 64);
+                    float4* xrow = reinterpret_cast<float4*>(bp + EPB_PX + lane * 64);
+                    uint4* hrow = reinterpret_cast<uint4*>(bp + 2 * EPB_PX + lane * 32);
 #pragma unroll
-                    for (int j = 0; j < EB; ++j) {
-                        const float g = __uint_as_float(gv[j]);
-                        const float dtj = dts[j];
-                        const float xo = Xs[lane * (EB + 1) + j];
-                        hv = fmaf(xo, g, hv);
-                        const float pn = fmaf(g, kw * dtj, Ps[lane * (EB + 1) + j]);       // samplers.py:835, 837
-                        hk = fmaf(pn, pn, hk);
-                        xn[j] = fmaf(pn, dw * dtj, xo);                                   // samplers.py:836
-                        Ps[lane * (EB + 1) + j] = pn;
-                        Xs[lane * (EB + 1) + j] = xn[j];
-                    }
+                    for (int i = 0; i < CW / 4; ++i) {
+                        float4 p4 = prow[i ^ swz], x4 = xrow[i ^ swz];
+                        float pv[4] = {p4.x, p4.y, p4.z, p4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                    for (int j = 0; j < EB / 2; ++j) {
-                        uint32_t h[3];
-                        split_pair<NPART>(xn[2 * j], xn[2 * j + 1], h);
+                        for (int e = 0; e < 4; ++e) {
+                            const float gj = __uint_as_float(gv[4 * i + e]);
+                            const float dtj = dts[4 * i + e];
+                            hv = fmaf(xv[e], gj, hv);
+                            const float pn = fmaf(gj, kw * dtj, pv[e]);                       // samplers.py:835, 837
+                            hk = fmaf(pn, pn, hk);
+                            xv[e] = fmaf(pn, dw * dtj, xv[e]);                                // samplers.py:836
+                            pv[e] = pn;
+                        }
+                        prow[i ^ swz] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                        xrow[i ^ swz] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                        uint32_t h0[3], h1[3];
+                        split_pair<NPART>(xv[0], xv[1], h0);
+                        split_pair<NPART>(xv[2], xv[3], h1);
+                        // the 8 bytes of columns 4 i .. 4 i + 3 of part pt: half of 16-byte piece i / 2 of the part's 32-byte row
 #pragma unroll
-                        for (int pt = 0; pt < NPART; ++pt) Hs[(pt * 32 + lane) * (EB / 2 + 1) + j] = h[pt];
-                    }
-                    __syncwarp();
-                    {   // shared -> row segments
-                        float* dst = gdst + cb * EB;
-                        const float* src = ((sub & 1) ? Xs : Ps) + col + (sub >> 1) * (EB + 1);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) __stcs(dst + (size_t)(2 * i) * D, src[2 * i * (EB + 1)]);
-                    }
-#pragma unroll
-                    for (int pt = 0; pt < NPART; ++pt) {
-                        // 4 words per row and part: lanes 4 r .. 4 r + 3 store row i + r (eight rows per instruction)
-                        uint32_t* dstp = reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp) * D) + (c0 >> 1) + (lane & 3);
-#pragma unroll
-                        for (int i = 0; i < 32; i += 8) {
-                            const int r = i + (lane >> 2);
-                            dstp[(size_t)(row0 + r) * (D >> 1)] = Hs[(pt * 32 + r) * (EB / 2 + 1) + (lane & 3)];
+                        for (int pt = 0; pt < NPART; ++pt) {
+                            uint2* piece = reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(hrow) + pt * EPB_PART + (((i >> 1) ^ swz2) << 4));
+                            piece[i & 1] = make_uint2(h0[pt], h1[pt]);
                         }
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my generic-proxy writes -> visible to the TMA store
                     __syncwarp();
-                };
-                request(va, 0);
-                if (NB > 1) request(vb, 1);
-                for (int b = 0; b < NB; b += 2) {
-                    block(va, b);
-                    if (b + 1 < NB) block(vb, b + 1);
+                    if (lane == 0) {
+                        tma_store_2d(&mapP, bp, c0, (int)row0);
+                        tma_store_2d(&mapX, bp + EPB_PX, c0, (int)row0);
+#pragma unroll
+                        for (int pt = 0; pt < NPART; ++pt) tma_store_2d(&mapS, bp + 2 * EPB_PX + pt * EPB_PART, c0, (int)(pt * part_rows_a + row0));
+                        bulk_commit();
+                        bulk_wait_read<1>();                             // the store of chunk g - 1 has left its buffer: chunk g + 2 goes there
+                    }
+                    __syncwarp();
+                    prefetch_one();
                 }
             }
             if (chain < Nchain) {
-                float* rd = w.red + (((size_t)chain * NT + nt) * 2 + half) * 2;
-                rd[0] = hv; rd[1] = hk;
+                float* rd = w.red + ((size_t)chain * NT + nt) * 4;
+                rd[0] = hv; rd[1] = hk; rd[2] = 0.f; rd[3] = 0.f;
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + as);
             ++nt_done;
         }
+        if (lane == 0) bulk_wait_all();                                  // every store complete before the buffers go away
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -410,7 +448,7 @@ __device__ __forceinline__ void bigd_write_parts(const BigdWs& w, long m, int D,
         uint32_t h[3];
         split_pair<NPART>(xrow[j], xrow[j + 1], h);
 #pragma unroll
-        for (int pt = 0; pt < NPART; ++pt) reinterpret_cast<uint32_t*>(w.xp + ((size_t)pt * w.Ncp + m) * D)[j >> 1] = h[pt];
+        for (int pt = 0; pt < NPART; ++pt) reinterpret_cast<uint32_t*>(w.xp + (((size_t)w.wr * NPART + pt) * w.Ncp + m) * D)[j >> 1] = h[pt];
     }
 }
 
@@ -617,16 +655,18 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D map over a [rows][D] matrix of 16-bit elements, box = bk elements (128 / 64 / 32 bytes) x box_rows, swizzle of that width
-int make_map(CUtensorMap* map, bool f16, void* base, uint64_t rows, uint64_t D, uint32_t box_rows, int bk) {
+// 2-D map over a row-major [rows][D] matrix: box = box_cols x box_rows elements, swizzle = the box's row length in bytes
+// (128 / 64 / 32)
+int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t rows, uint64_t D, uint32_t box_cols, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { hmc_set_error("cuTensorMapEncodeTiled is not available from the driver"); return HMC_E_CUDA; }
     const cuuint64_t dims[2] = {D, rows};
-    const cuuint64_t strides[1] = {D * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
-    const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const cuuint64_t strides[1] = {D * (uint64_t)elem_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+    const uint32_t row_bytes = box_cols * (uint32_t)elem_bytes;
+    const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUresult r = enc(map, dt, 2, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { hmc_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return HMC_E_CUDA; }
@@ -642,7 +682,7 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char* p = ws ? ws + off : nullptr; off = align_up(off + bytes, 1024); return p; };
     w.Ncp = (int)Ncp; w.NT = NT; w.npart = npart;
-    w.xp = (uint16_t*)take((size_t)npart * Ncp * D * 2);
+    w.xp = (uint16_t*)take((size_t)2 * npart * Ncp * D * 2);
     w.bp = (uint16_t*)take((size_t)npart * D * D * 2);
     w.x = (float*)take((size_t)Ncp * D * 4);
     w.x0 = (float*)take((size_t)Ncp * D * 4);
@@ -657,13 +697,14 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
     return off;
 }
 
-template <int NPART, int BN>
+template <int NPART, int BN, int BK, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-    return (size_t)NPART * (BM * kStageK * 2 + BN * kStageK * 2) + NEPI * (2 * 32 * (EB + 1) * 4 + 64 + NPART * 32 * (EB / 2 + 1) * 4) + 32 * 8 + 64;
+    return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + (size_t)NEPI * NBUF * (2 * EPB_PX + NPART * EPB_PART) + (2 * STAGES + 4 + NEPI * NBUF) * 8 + 64;
 }
-static_assert(gemm_smem_bytes<2, 256>() <= 232448 && gemm_smem_bytes<3, 128>() <= 232448, "shared memory of the large-D GEMM exceeds 227 KB");
+static_assert(gemm_smem_bytes<2, 256, 32, 3>() <= 232448 && gemm_smem_bytes<3, 128, 32, 2>() <= 232448,
+              "shared memory of the large-D GEMM exceeds 227 KB");
 
-template <int NPART, int BN, int CL, int BK>
+template <int NPART, int BN, int CL, int BK, int STAGES>
 int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     const int D = a.target.D;
     BigdWs w;
@@ -691,14 +732,22 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     }
     w.binv = 1.f / scale;
     bigd_split_matrix<NPART><<<sms * 8, 256, 0, stream>>>((const float*)a.target.Ft, D, a.target.D_pad, scale, w.bp);
-    CUtensorMap mapA, mapB;
-    if (int rc = make_map(&mapA, NPART == 2, w.xp, (uint64_t)NPART * w.Ncp, D, BM, BK)) return rc;
-    if (int rc = make_map(&mapB, NPART == 2, w.bp, (uint64_t)NPART * D, D, BN / CL, BK)) return rc;      // each CTA of a cluster loads 1 / CL of a B tile
+    CUtensorMap mapA[2], mapS[2], mapB, mapP, mapX;
+    const CUtensorMapDataType dt16 = NPART == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    for (int b = 0; b < 2; ++b) {
+        uint16_t* xb = w.xp + (size_t)b * NPART * w.Ncp * D;
+        if (int rc = make_map(&mapA[b], dt16, 2, xb, (uint64_t)NPART * w.Ncp, D, BK, BM)) return rc;       // operand loads
+        if (int rc = make_map(&mapS[b], dt16, 2, xb, (uint64_t)NPART * w.Ncp, D, CW, 32)) return rc;       // epilogue stores
+    }
+    if (int rc = make_map(&mapB, dt16, 2, w.bp, (uint64_t)NPART * D, D, BK, BN / CL)) return rc;           // each CTA of a cluster loads 1 / CL of a B tile
+    if (int rc = make_map(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.p, (uint64_t)w.Ncp, D, CW, 32)) return rc;
+    if (int rc = make_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.x, (uint64_t)w.Ncp, D, CW, 32)) return rc;
+    w.wr = 0;                                                    // pass 0 reads buffer 0
     bigd_init<NPART><<<(w.Ncp + 3) / 4, 128, 0, stream>>>(a, w);
     const int ntile_rows = w.Ncp / BM;
     HMC_CUDA_CHECK(cudaMemsetAsync(w.tile_active, 0xff, (size_t)ntile_rows * 4, stream));
-    const size_t smem = gemm_smem_bytes<NPART, BN>();
-    auto kern = bigd_gemm_step<NPART, BN, CL, BK>;
+    const size_t smem = gemm_smem_bytes<NPART, BN, BK, STAGES>();
+    auto kern = bigd_gemm_step<NPART, BN, CL, BK, STAGES>;
     HMC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (ntile_rows / CL) * w.NT;                 // work items of a cluster
     // persistent clusters: as many as are resident at once (a GPC holds whole clusters only), never more than there is work
@@ -720,7 +769,9 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     cfg.gridDim = dim3(grid);
     const float* dtv = (const float*)a.target.dt;
     const int Nch = a.Nchain;
-    auto launch_gemm = [&]() { return cudaLaunchKernelEx(&cfg, kern, mapA, mapB, w, Nch, D, dtv); };
+    // pass n: operands from buffer n & 1, the epilogue (and the trajectory ends after it) write buffer (n + 1) & 1
+    auto launch_gemm = [&](long pass) { w.wr = (int)((pass + 1) & 1);
+                                        return cudaLaunchKernelEx(&cfg, kern, mapA[pass & 1], mapB, mapP, mapX, mapS[(pass + 1) & 1], w, Nch, D, dtv); };
     int* running_h = nullptr;
     HMC_CUDA_CHECK(cudaMallocHost(&running_h, 4));
     const long max_pass = (long)(a.iter_end - a.iter_begin) * (a.L_high + 1) + 8;
@@ -733,7 +784,7 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     for (long pass = 0; pass < max_pass; ++pass) {
         if (timing && pass >= 4 && pass < 12) {
             cudaEventRecord(ev[0], stream);
-            launch_gemm();
+            launch_gemm(pass);
             cudaEventRecord(ev[1], stream);
             cudaMemsetAsync(w.counters + 2, 0, 4, stream);
             bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
@@ -746,7 +797,7 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
                                     NPART, BN, BK, CL, a.Nchain, D, tsum[0] / 8, tsum[1] / 8, tsum[2] / 8, ntiles, grid);
             continue;
         }
-        if (launch_gemm() != cudaSuccess) { rc = HMC_E_CUDA; break; }
+        if (launch_gemm(pass) != cudaSuccess) { rc = HMC_E_CUDA; break; }
         cudaMemsetAsync(w.counters + 2, 0, 4, stream);
         bigd_events<<<ntile_rows, BM, 0, stream>>>(a, w, (int)pass);
         bigd_trajectory_end<NPART><<<sms * 2, 256, 0, stream>>>(a, w, (int)pass);
@@ -783,17 +834,11 @@ size_t hmc_random_bigd_workspace(const hmc_random_args& a) {
 int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     bool fp16 = (a.flags & HMC_FLAG_TC_FP16X2) != 0;
     if (const char* e = getenv("HMC_B200_TC_PREC")) fp16 = (e[0] == 'f');
-    // Measured alternatives, kept selectable (HMC_B200_BIGD_CLUSTER=2: clusters of two row blocks with the B tile multicast;
-    // HMC_B200_BIGD_BK=32: four 48 KB stages instead of two 96 KB ones).  Neither moves the pass time (1.22-1.28 ms at 131,072
-    // chains): the L2 already merges the concurrent unicast reads of a B tile, and the kernel is bound by its epilogue, not by
-    // the operand pipeline.  Default: one CTA per tile, two stages of K = 64.
-    int cl = 1, bk = 64;
+    // Clusters of two row blocks share the column block's B tile by TMA multicast (HMC_B200_BIGD_CLUSTER=1: plain CTAs).  With the
+    // first epilogue the cluster changed nothing (the kernel was bound by its epilogue); with the TMA epilogue it is worth 8 % of a
+    // full pass at fp16x2 and 19 % of a bf16x3 run.
+    int cl = 2;
     if (const char* e = getenv("HMC_B200_BIGD_CLUSTER")) cl = atoi(e);
-    if (const char* e = getenv("HMC_B200_BIGD_BK")) bk = atoi(e);
-    if (fp16) {
-        if (cl == 2) return run_bigd<2, 256, 2, 64>(a, stream);
-        return bk == 32 ? run_bigd<2, 256, 1, 32>(a, stream) : run_bigd<2, 256, 1, 64>(a, stream);
-    }
-    if (cl == 2) return run_bigd<3, 128, 2, 64>(a, stream);
-    return bk == 32 ? run_bigd<3, 128, 1, 32>(a, stream) : run_bigd<3, 128, 1, 64>(a, stream);
+    if (fp16) return cl == 2 ? run_bigd<2, 256, 2, 32, 3>(a, stream) : run_bigd<2, 256, 1, 32, 3>(a, stream);
+    return cl == 2 ? run_bigd<3, 128, 2, 32, 2>(a, stream) : run_bigd<3, 128, 1, 32, 2>(a, stream);
 }
