@@ -311,8 +311,8 @@ def secondary_measurements(torch, dist, S, U, L, lib, rank, world, dev, log):
         except Exception:
             pk = 2250.0 * world
         out.append({"name": "bigd_config5", "what": "dense-covariance MVN D=1024 (log-uniform spectrum on [0.05,100], random rotation), %d chains/GPU, "
-                    "2 iterations, L in [100,500), dt=0.1: one tcgen05 GEMM over all chains per leapfrog step (TMA operands, fp16x2 split, "
-                    "leapfrog fused into the epilogue); all ranks' work over the slowest rank's kernel time" % Nb,
+                    "2 iterations, L in [100,500), dt=0.1: one tcgen05 GEMM over all chains per leapfrog step (TMA operands with the B tile multicast "
+                    "to clusters of two, fp16x2 split, leapfrog fused into a TMA-fed epilogue); all ranks' work over the slowest rank's kernel time" % Nb,
                     "seconds": t, "kernel_ms": H.kernel_ms, "accept_R": H.accept_R, "tc_precision": H.tc_precision,
                     "leapfrog_grad_evals_per_sec": H.sum_L / (H.kernel_ms * 1e-3),
                     "roofline": {"bound": "tensor", "achieved": alg, "peak": pk, "unit": "TFLOP/s", "frac": alg / pk,

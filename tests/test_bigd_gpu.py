@@ -99,3 +99,29 @@ def test_bigd_chain0_trace_and_auto_dispatch():
     np.testing.assert_allclose(np.concatenate(F.phi_q), np.concatenate(G.phi_q), rtol=0, atol=2e-4)
     np.testing.assert_array_equal(F.decision_chain, G.decision_chain)
     assert F.sum_L == G.sum_L
+
+
+@pytest.mark.parametrize("prec", ["fp16x2", "bf16x3"])
+def test_bigd_full_grid_run_equals_its_own_shards(prec):
+    """Scale property (no oracle needed): a chain's trajectory does not depend on which other chains share the launch.  32,768
+    chains at D = 512 are 512 (row block, column tile) work items on the persistent grid -- several rounds per CTA, column tiles
+    of one row block on different CTAs -- and must reproduce, bit for bit, what shards of 1,024 chains with the same global
+    chain ids give on their own.  The first version of the kernel failed exactly this at scale: the epilogue of one column tile
+    overwrote the split position (the A operand) while the sibling column tiles of the row block were still reading it, which
+    showed as an acceptance of 0.69-0.72 instead of 1.0 on BASELINE config 5; the operand is double-buffered by pass now."""
+    import samplers as S
+    D, Nchain, Niter = 512, 32768, 2
+    tgt, _ = _dense_target(D, 4, 0.2, 30.0)
+    spec = S.MVNSpec(tgt.q0, tgt.inv_cov0, tgt.const)
+    q_start = (tgt.q0 + np.random.RandomState(8).standard_normal((Nchain, D)) * 2.0).astype(np.float32)
+    kw = dict(Niter=Niter, thin_rate=1, warm_up_num=0, sampler_type="Random", dt=0.1, L_low=30, L_high=60, dtype="float32", seed=4,
+              target=spec, kernel="bigd", tc_precision=prec)
+    F = S.HMC_sampler(D, None, None, Nchain=Nchain, **kw)
+    F.gen_sample(q_start, verbose=False, quiet=True)
+    full_q, full_E = F.q_chain, F.E_chain
+    assert np.all(np.isfinite(full_q))
+    for lo in (0, 16384 + 128, Nchain - 1024):
+        Sh = S.HMC_sampler(D, None, None, Nchain=1024, chain_id0=lo, **kw)
+        Sh.gen_sample(q_start[lo:lo + 1024], verbose=False, quiet=True)
+        np.testing.assert_array_equal(Sh.q_chain, full_q[lo:lo + 1024])
+        np.testing.assert_array_equal(Sh.E_chain, full_E[lo:lo + 1024])
