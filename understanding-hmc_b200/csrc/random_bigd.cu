@@ -303,13 +303,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                                      return (ch < Nchain) ? w.mode[ch] : (int)MD_IDLE; };
         auto is_live = [&](int md) { return __any_sync(HMC_FULL_MASK, md == MD_FIRST || md == MD_MID || md == MD_LAST) != 0; };
         auto next_live = [&](int tt) { for (tt += ncl; tt < ntiles; tt += ncl) if (item_active(tt / NT) && is_live(tile_md(tt))) break; return tt; };
-        auto issue_chunk = [&](int tt, int c, uint32_t g) {      // lane 0: chunk c of tile tt is the g-th chunk of this warp's stream
+        // chunk c of tile tt is the g-th chunk of this warp's stream; lanes 0 and 1 issue the two loads in ONE warp instruction (a
+        // lane-serial sequence of TMA instructions was 30 % of the epilogue warps' stall samples)
+        auto issue_chunk = [&](int tt, int c, uint32_t g) {
             const int buf = g % NBUF;
             unsigned char* bp = ebase + buf * EPI_BUF_BYTES;
             const int col0 = (tt % NT) * BN + c * CW, row0 = ((tt / NT) * CL + crank) * BM + quarter * 32;
-            mbar_expect_tx(ef + buf, 2 * EPB_PX);
-            tma_load_2d(bp, &mapP, col0, row0, ef + buf);
-            tma_load_2d(bp + EPB_PX, &mapX, col0, row0, ef + buf);
+            if (lane == 0) mbar_expect_tx(ef + buf, 2 * EPB_PX);
+            __syncwarp();
+            if (lane < 2) tma_load_2d(bp + lane * EPB_PX, lane == 0 ? &mapP : &mapX, col0, row0, ef + buf);
         };
         // prefetch cursor: (pf_t, pf_c) = the next chunk to request, pf_g its number in the stream
         int pf_t = cid - ncl;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
         uint32_t pf_g = 0, g = 0;
         auto prefetch_one = [&]() {
             if (pf_t >= ntiles) return;
-            if (lane == 0) issue_chunk(pf_t, pf_c, pf_g);
+            issue_chunk(pf_t, pf_c, pf_g);
             ++pf_g;
             if (++pf_c == NCH) { pf_c = 0; pf_t = next_live(pf_t); }
         };
@@ -390,13 +392,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my generic-proxy writes -> visible to the TMA store
                     __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&mapP, bp, c0, (int)row0);
-                        tma_store_2d(&mapX, bp + EPB_PX, c0, (int)row0);
-#pragma unroll
-                        for (int pt = 0; pt < NPART; ++pt) tma_store_2d(&mapS, bp + 2 * EPB_PX + pt * EPB_PART, c0, (int)(pt * part_rows_a + row0));
-                        bulk_commit();
-                        bulk_wait_read<1>();                             // the store of chunk g - 1 has left its buffer: chunk g + 2 goes there
+                    if (lane < 2 + NPART) {                              // lanes 0, 1: momentum, position; lanes 2..: the parts -- one instruction
+                        const CUtensorMap* mp = lane == 0 ? &mapP : (lane == 1 ? &mapX : &mapS);
+                        const unsigned char* src = bp + (lane < 2 ? lane * EPB_PX : 2 * EPB_PX + (lane - 2) * EPB_PART);
+                        const int r = (int)row0 + (lane < 2 ? 0 : (lane - 2) * (int)part_rows_a);
+                        tma_store_2d(mp, src, c0, r);
+                        bulk_commit();                                   // (bulk groups are per thread: each storing lane tracks its own)
+                        bulk_wait_read<1>();                             // the stores of chunk g - 1 have left their buffer: chunk g + 2 goes there
                     }
                     __syncwarp();
                     prefetch_one();
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             if (lane == 0) mbar_arrive(tempty + as);
             ++nt_done;
         }
-        if (lane == 0) bulk_wait_all();                                  // every store complete before the buffers go away
+        if (lane < 2 + NPART) bulk_wait_all();                           // every store complete before the buffers go away
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
