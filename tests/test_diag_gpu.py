@@ -21,7 +21,8 @@ def _ar1(Nchain, N, D, phi, seed, offset=0.0):
                                    (16, 1000, 2, 0.99),
                                    # float32 with D % 4 == 0: the all-lags FFT pass (csrc/diag_fft.cu), straight away for
                                    # n >= 192, after one windowed chunk below that
-                                   (10, 400, 8, 0.9), (6, 1000, 4, 0.99), (12, 200, 100, 0.8), (5, 1024, 12, 0.97), (40, 801, 100, 0.95)])
+                                   (10, 400, 8, 0.9), (6, 1000, 4, 0.99), (12, 200, 100, 0.8), (5, 1024, 12, 0.97), (40, 801, 100, 0.95),
+                                   (4, 1100, 4, 0.9)])     # n = 550 > 512: beyond the transform length, back on the windowed kernels
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_convergence_stats_matches_oracle(shape, dtype):
     import utils as U
