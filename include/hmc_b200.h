@@ -86,6 +86,15 @@ typedef struct hmc_target {
 } hmc_target;
 
 /*
+ * HMC_sampler.leap_frog (samplers.py:831-839) for B independent (p, q) pairs, rows of [B][D] arrays in `dtype`:
+ *   p' = p - dt F (q - mu) / 2,  q' = q + dt p',  p'' = p' - dt F (q' - mu) / 2      (F = M^-1 P; q moves by p, not M^-1 p: quirk Q9)
+ * `nsteps` >= 1 repetitions.  The public primitive of the path (the samplers fuse it into their trajectory kernels, one gradient
+ * per step); D <= 1024.
+ */
+int hmc_leap_frog(int32_t dtype, const hmc_target* target, int64_t B, const void* p_old, const void* q_old, void* p_new, void* q_new,
+                  int32_t nsteps, void* cuda_stream);
+
+/*
  * Random-trajectory-length sampler: replaces HMC_sampler.gen_sample_random (samplers.py:387-491) together
  * with K / E / p_sample / leap_frog (samplers.py:811-839) for chains [0, Nchain) of this device, global
  * chain ids chain_id0 + m (the Philox streams are keyed by GLOBAL chain id, so results do not depend on how

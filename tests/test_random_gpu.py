@@ -210,6 +210,38 @@ def test_fixed_sampler_matches_reference_constant_length_run():
     assert P.N_total_steps == 8 * (1 + 2 * 20) + 4 * 49 * 8 * 20
 
 
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-6)])
+def test_leap_frog_primitive_matches_oracle(dtype, tol):
+    """HMC_sampler.leap_frog (samplers.py:831-839) through the C-ABI (hmc_leap_frog): single pairs and batches, scalar and
+    per-dimension dt, identity and dense momentum metric (force times M^-1, q moved by p: Q9), against the oracle's statement-by-
+    statement restatement."""
+    import samplers as S
+    rng = np.random.RandomState(3)
+    for D, dense_metric, vec_dt in [(2, False, False), (10, True, True), (100, False, False), (100, True, True), (300, False, True)]:
+        cov = O.equicorrelated_cov(D, 0.6) if D != 300 else np.diag(rng.uniform(0.5, 2.0, D))
+        tgt = O.MVNTarget(rng.standard_normal(D) * 0.3, cov)
+        A = rng.standard_normal((D, D)) * 0.2
+        cov_p = (np.eye(D) + A @ A.T) if dense_metric else None
+        dt = (0.05 + 0.1 * rng.uniform(size=D)) if vec_dt else 0.1
+        H = S.HMC_sampler(D, tgt.V, tgt.dVdq, Nchain=2, Niter=1, sampler_type="Random", dt=dt, global_dt=not vec_dt, L_low=1, L_high=2,
+                          cov_p=cov_p, dtype=dtype)
+        inv_cov_p = np.eye(D) if cov_p is None else np.linalg.inv(cov_p)
+        p, q = rng.standard_normal((7, D)), rng.standard_normal((7, D)) * 1.5 + tgt.q0
+        pn, qn = H.leap_frog(p, q)
+        for b in range(7):
+            pw, qw = O.leap_frog(p[b], q[b], dt, inv_cov_p, tgt.dVdq)
+            scale = max(1.0, np.abs(pw).max(), np.abs(qw).max())
+            assert np.abs(pn[b] - pw).max() < tol * scale and np.abs(qn[b] - qw).max() < tol * scale
+        p1, q1 = H.leap_frog(p[0], q[0])                                   # a single pair keeps its shape
+        assert p1.shape == q1.shape == (D,)
+        np.testing.assert_array_equal(p1, pn[0]); np.testing.assert_array_equal(q1, qn[0])
+        p3, q3 = H.leap_frog(p, q, nsteps=3)                               # repeated steps = three calls
+        pr, qr = p, q
+        for _ in range(3):
+            pr, qr = H.leap_frog(pr, qr)
+        np.testing.assert_allclose(p3, pr, rtol=0, atol=10 * tol); np.testing.assert_allclose(q3, qr, rtol=0, atol=10 * tol)
+
+
 def test_target_extraction_and_errors():
     import samplers as S
     import hmc_b200_lib as L

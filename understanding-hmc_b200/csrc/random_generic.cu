@@ -208,7 +208,80 @@ int dispatch_generic(const hmc_random_args& a, cudaStream_t stream) {
     return HMC_E_UNSUPPORTED;
 }
 
+// HMC_sampler.leap_frog (/root/reference/samplers.py:831-839) for a batch of (p, q) pairs: one warp per pair, `nsteps` steps as
+// the reference writes one (force F (q - mu) = M^-1 P (q - mu) at both ends of every step, no reuse between steps: the public
+// primitive, not the fused loop).  Matrices are read from global memory / L2 (small batches: a parity and API entry point).
+template <typename T, int NJ>
+__global__ void __launch_bounds__(128) hmc_leap_frog_kernel(hmc_target t, long B, const T* __restrict__ p_old, const T* __restrict__ q_old,
+                                                            T* __restrict__ p_new, T* __restrict__ q_new, int nsteps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = t.D, Dp = t.D_pad, lane = threadIdx.x & 31;
+    T* xs = (T*)smem_raw + (size_t)(threadIdx.x >> 5) * Dp;
+    const long m = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= B) return;
+    const T* Ft = (const T*)t.Ft;
+    T q[NJ], p[NJ], f[NJ], d[NJ], mu[NJ], dt[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+        const int j = hmc_dim<NJ>(lane, i);
+        mu[i] = (j < D) ? ((const T*)t.mu)[j] : T(0);
+        dt[i] = (j < D) ? ((const T*)t.dt)[j] : T(0);
+        q[i] = (j < D) ? q_old[(size_t)m * D + j] : T(0);
+        p[i] = (j < D) ? p_old[(size_t)m * D + j] : T(0);
+        f[i] = T(0);
+    }
+    auto force = [&]() {
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) d[i] = q[i] - mu[i];
+        matvec_t<T, NJ, false>(Ft, D, Dp, d, f, lane, xs);
+    };
+    for (int s = 0; s < nsteps; ++s) {
+        force();
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) {
+            p[i] = p[i] - dt[i] * f[i] / T(2);                          // samplers.py:835
+            q[i] = q[i] + dt[i] * p[i];                                 // samplers.py:836
+        }
+        force();
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) p[i] = p[i] - dt[i] * f[i] / T(2); // samplers.py:837
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+        const int j = hmc_dim<NJ>(lane, i);
+        if (j < D) { p_new[(size_t)m * D + j] = p[i]; q_new[(size_t)m * D + j] = q[i]; }
+    }
+}
+
+template <typename T, int NJ>
+int launch_leap_frog(const hmc_target& t, long B, const void* p_old, const void* q_old, void* p_new, void* q_new, int nsteps, cudaStream_t stream) {
+    const int warps = 4;
+    const size_t smem = (size_t)warps * t.D_pad * sizeof(T);
+    hmc_leap_frog_kernel<T, NJ><<<(unsigned)((B + warps - 1) / warps), warps * 32, smem, stream>>>(t, B, (const T*)p_old, (const T*)q_old, (T*)p_new, (T*)q_new, nsteps);
+    HMC_CUDA_CHECK(cudaGetLastError());
+    return HMC_OK;
+}
+
+template <typename T>
+int dispatch_leap_frog(const hmc_target& t, long B, const void* p_old, const void* q_old, void* p_new, void* q_new, int nsteps, cudaStream_t stream) {
+    if (t.D <= 32) return launch_leap_frog<T, 1>(t, B, p_old, q_old, p_new, q_new, nsteps, stream);
+    if (t.D <= 128) return launch_leap_frog<T, 4>(t, B, p_old, q_old, p_new, q_new, nsteps, stream);
+    if (t.D <= 256) return launch_leap_frog<T, 8>(t, B, p_old, q_old, p_new, q_new, nsteps, stream);
+    if (t.D <= 1024) return launch_leap_frog<T, 32>(t, B, p_old, q_old, p_new, q_new, nsteps, stream);
+    hmc_set_error("hmc_leap_frog supports D <= 1024 (got %d)", t.D);
+    return HMC_E_UNSUPPORTED;
+}
+
 }  // namespace
+
+extern "C" int hmc_leap_frog(int32_t dtype, const hmc_target* target, int64_t B, const void* p_old, const void* q_old, void* p_new, void* q_new,
+                             int32_t nsteps, void* cuda_stream) {
+    if (!target || !p_old || !q_old || !p_new || !q_new || !target->Ft || !target->mu || !target->dt) { hmc_set_error("hmc_leap_frog: NULL buffer"); return HMC_E_BADARG; }
+    if ((dtype != HMC_F32 && dtype != HMC_F64) || B < 1 || nsteps < 1 || target->D < 1) { hmc_set_error("hmc_leap_frog: need dtype HMC_F32 / HMC_F64, B >= 1, nsteps >= 1"); return HMC_E_BADARG; }
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (dtype == HMC_F32) return dispatch_leap_frog<float>(*target, (long)B, p_old, q_old, p_new, q_new, nsteps, stream);
+    return dispatch_leap_frog<double>(*target, (long)B, p_old, q_old, p_new, q_new, nsteps, stream);
+}
 
 int hmc_random_run_generic(const hmc_random_args& a, cudaStream_t stream) {
     if (a.dtype == HMC_F32) return dispatch_generic<float>(a, stream);

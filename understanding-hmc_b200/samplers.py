@@ -558,6 +558,27 @@ class HMC_sampler(sampler):
     def p_sample(self):
         return np.random.multivariate_normal(np.zeros(self.D), self.cov_p, size=1)
 
+    def leap_frog(self, p_old, q_old, nsteps=1):
+        """One leapfrog step (samplers.py:831-839) -- on the GPU (``hmc_leap_frog``), for a single (p, q) pair or a batch of rows:
+        p' = p - dt M^-1 dVdq(q) / 2, q' = q + dt p', p'' = p' - dt M^-1 dVdq(q') / 2, as the reference writes it (force times
+        M^-1, q moved by p: Q9).  Returns (p_new, q_new) as float64 numpy arrays of the input's shape.  ``nsteps`` > 1 repeats the
+        step (this repo's extension)."""
+        import torch
+        lib = _L.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t, keep, tdt = self._build_target(torch, dev)
+        p = np.asarray(p_old, dtype=float)
+        q = np.asarray(q_old, dtype=float)
+        shape = q.shape
+        p2, q2 = p.reshape(-1, self.D), q.reshape(-1, self.D)
+        assert p2.shape == q2.shape
+        pd = torch.from_numpy(np.ascontiguousarray(p2)).to(device=dev, dtype=tdt)
+        qd = torch.from_numpy(np.ascontiguousarray(q2)).to(device=dev, dtype=tdt)
+        pn, qn = torch.empty_like(pd), torch.empty_like(qd)
+        _L.check(lib.hmc_leap_frog(_L.HMC_F32 if self.dtype == "float32" else _L.HMC_F64, t, q2.shape[0], _L.ptr(pd), _L.ptr(qd),
+                                   _L.ptr(pn), _L.ptr(qn), int(nsteps), _L.current_stream_ptr()))
+        return pn.double().cpu().numpy().reshape(shape), qn.double().cpu().numpy().reshape(shape)
+
     def make_movie(self, title_prefix, q0=None, cov0=None, plot_cov=True, qmin=-3, qmax=3):
         """Slide deck of chain-0 trajectories (samplers.py:843-871): presentation, out of scope; the captured
         inputs ``phi_q`` / ``decision_chain`` are produced by the kernel."""
