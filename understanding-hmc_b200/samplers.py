@@ -92,7 +92,7 @@ class sampler(object):
         # layout (Nchain, L_chain, D) are materialised on first access.
         self._q_dev = None
         self._q_host = None
-        self.lnL_chain = None
+        self._lnL_host = None
         self.R_q = None
         self.R_lnL = None
         self.n_eff_q = None
@@ -263,6 +263,13 @@ class HMC_sampler(sampler):
             self._E_host = np.zeros((self.Nchain, self.L_chain, 1)) if self._E_dev is None else \
                 self._E_dev.cpu().numpy()[:, :, None]
         return self._E_host
+
+    @property
+    def lnL_chain(self):
+        """(Nchain, L_chain, 1) zeros, as the reference allocates it (samplers.py:34; its live samplers never fill it)."""
+        if self._lnL_host is None:
+            self._lnL_host = np.zeros((self.Nchain, self.L_chain, 1))
+        return self._lnL_host
 
     @property
     def dE_chain(self):
