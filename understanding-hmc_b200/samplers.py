@@ -439,8 +439,9 @@ class HMC_sampler(sampler):
         ev1.record()
         ev1.synchronize()
         self.kernel_ms = ev0.elapsed_time(ev1)
-        if (a.flags & _L.FLAG_TC_FP16X2) and self.kernel in ("auto", "tc") and D == 100 and \
-                int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0:
+        tc_ran = self.dtype == "float32" and self._cov_p_identity and D % 4 == 0 and \
+            ((self.kernel == "tc" and 4 <= D <= 100) or (self.kernel == "auto" and 52 <= D <= 100))       # csrc/api.cu AUTO rule
+        if (a.flags & _L.FLAG_TC_FP16X2) and tc_ran and int(keep["state_g"].view(torch.int32)[16 + Nc].item()) != 0:
             # a start point left the range of the fp16 split (tensor-core kernel only): repeat with the bf16x3 split
             self.tc_precision = "bf16x3"
             return self.gen_sample_random(q_start, N_save_chain0, verbose, quiet)
