@@ -31,6 +31,8 @@
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include <cstdio>
+#include <vector>
+#include <algorithm>
 
 namespace {
 
@@ -142,6 +144,10 @@ struct BigdWs {                      // workspace carved by the host (all device
     uint16_t* xp;                    // [2][NPART][Ncp][D]  split position = A operand: pass n reads buffer n & 1 and writes the other one
                                      // (the column tiles of a row block read ALL its columns while one of them already writes its own)
     int wr;                          // buffer the parts of the next pass go to (set per launch)
+    int* perm;                       // [Ncp] row -> local chain index (-1: padding row).  Rows are chains SORTED by the number of passes
+                                     // their run needs (the trajectory lengths are a pure function of (seed, chain, iteration)), so the
+                                     // 128 chains of a row block end together and finished blocks drop out of the GEMM early
+    int* plan;                       // [Ncp] passes a chain needs: sum over its iterations of L + 1
     uint16_t* bp;                    // [NPART][D][D]    split force matrix (x 2^s for the fp16 split) = B operand
     float* x;                        // [Ncp][D] shifted position q - mu
     float* x0;                       // [Ncp][D] position at the start of the running trajectory
@@ -454,77 +460,94 @@ __device__ __forceinline__ void bigd_write_parts(const BigdWs& w, long m, int D,
     }
 }
 
+// passes the run of a chain needs (one per leapfrog point: L + 1 per iteration; rejections add a few): the key the rows are sorted by
+__global__ void __launch_bounds__(256) bigd_plan(hmc_random_args a, int* __restrict__ plan) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.Nchain) return;
+    const uint64_t gid = (uint64_t)(a.chain_id0 + c);
+    int total = 0;
+    for (int it = a.iter_begin + 1; it <= a.iter_end; ++it) {
+        int L; double u;
+        if (a.L_tape) L = a.L_tape[(size_t)c * a.Niter + it - 1];
+        else hmc_scalar_draws(a.seed, gid, (uint32_t)it, a.L_low, a.L_high, &L, &u);
+        total += L + 1;
+    }
+    plan[c] = total;
+}
+
 // chain start (samplers.py:411-420) or resume from state_q: one warp per chain
 template <int NPART>
 __global__ void __launch_bounds__(128) bigd_init(hmc_random_args a, BigdWs w) {
     const int lane = threadIdx.x & 31, D = a.target.D;
-    const long m = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long m = (long)blockIdx.x * 4 + (threadIdx.x >> 5);            // row of the workspace
     if (m >= w.Ncp) return;
     float* xr = w.x + (size_t)m * D;
     float* x0r = w.x0 + (size_t)m * D;
     float* pr = w.p + (size_t)m * D;
-    if (m >= a.Nchain) {                                     // padding rows of the last tile
+    const long c = w.perm[m];                                            // the chain that lives in this row
+    if (c < 0) {                                             // padding rows of the last tile
         for (int j = lane; j < D; j += 32) { xr[j] = 0.f; x0r[j] = 0.f; pr[j] = 0.f; }
         bigd_write_parts<NPART>(w, m, D, lane, xr);
         if (lane == 0) { w.mode[m] = MD_IDLE; w.it[m] = a.iter_end + 1; }
         return;
     }
     const bool fresh = a.iter_begin == 0;
-    const float* src = (fresh ? (const float*)a.q_start : (const float*)a.state_q) + (size_t)m * D;
+    const float* src = (fresh ? (const float*)a.q_start : (const float*)a.state_q) + (size_t)c * D;
     const float* mu = (const float*)a.target.mu;
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;
     const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;
     for (int j = lane; j < D; j += 32) {
         const float v = src[j];
-        if (fresh) ((float*)a.q_chain)[(size_t)m * Lrow * D + j] = v;              // samplers.py:413
+        if (fresh) ((float*)a.q_chain)[(size_t)c * Lrow * D + j] = v;              // samplers.py:413
         xr[j] = v - mu[j]; x0r[j] = v - mu[j];
     }
     __syncwarp();
     bigd_write_parts<NPART>(w, m, D, lane, xr);
     int L = 1; float lnu = 0.f;
     float K0 = 0.f;
-    if (fresh) K0 = bigd_draw(a, m, 0, lane, nullptr, &L, &lnu);                   // samplers.py:415 (K only)
+    if (fresh) K0 = bigd_draw(a, c, 0, lane, nullptr, &L, &lnu);                   // samplers.py:415 (K only)
     const int it = a.iter_begin + 1;
-    const float Kn = bigd_draw(a, m, it, lane, pr, &L, &lnu);                      // samplers.py:431, 441, 461
+    const float Kn = bigd_draw(a, c, it, lane, pr, &L, &lnu);                      // samplers.py:431, 441, 461
     if (lane == 0) {
         w.mode[m] = (it <= a.iter_end) ? MD_FIRST : MD_IDLE;
         w.l[m] = 0; w.L[m] = L; w.it[m] = it; w.init[m] = fresh ? 1 : 0;
         w.K_new[m] = Kn; w.K0[m] = K0; w.lnu[m] = lnu;
-        w.E_init[m] = 0.f; w.E_prev[m] = fresh ? 0.f : (float)a.state_eprev[m];
-        if (fresh && a.decision_chain && a.chain_id0 + m == 0) a.decision_chain[a.N_save_chain0] = 0;
+        w.E_init[m] = 0.f; w.E_prev[m] = fresh ? 0.f : (float)a.state_eprev[c];
+        if (fresh && a.decision_chain && a.chain_id0 + c == 0) a.decision_chain[a.N_save_chain0] = 0;
     }
 }
 
 // per-chain bookkeeping after a pass (one thread per chain, one block per 128-chain tile)
 __global__ void __launch_bounds__(BM) bigd_events(hmc_random_args a, BigdWs w, int pass) {
-    const long m = (long)blockIdx.x * BM + threadIdx.x;
+    const long m = (long)blockIdx.x * BM + threadIdx.x;                              // row (the grid covers the Ncp rows exactly)
     const int D = a.target.D;
     const long Lc = 1 + (a.Niter - a.warm_up_num) / a.thin_rate;
     const long Lrow = a.store_ring > 0 ? a.store_ring : Lc;
     if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[(pass + 1) & 1] = 0;       // list length of the NEXT pass
-    int md = (m < a.Nchain) ? w.mode[m] : MD_IDLE;
+    int md = w.mode[m];                                                              // (padding rows are MD_IDLE from the start)
+    const long c = w.perm[m];                                                        // chain of this row: indexes the outputs
     unsigned long long acc_warm = 0, acc_post = 0, sL = 0, sL2 = 0;
     if (md == MD_FIRST || md == MD_MID || md == MD_LAST) {
         float hv = 0.f, hk = 0.f;
         for (int t = 0; t < 2 * w.NT; ++t) { hv += w.red[((size_t)m * 2 * w.NT + t) * 2]; hk += w.red[((size_t)m * 2 * w.NT + t) * 2 + 1]; }
         const float V = fmaf(0.5f * w.binv, hv, (float)a.target.v_const);           // V(q) at the point the gradient was taken
         const int it = w.it[m];
-        const bool tr = a.phi_q && (a.chain_id0 + m) == 0 && it <= a.N_save_chain0;
+        const bool tr = a.phi_q && (a.chain_id0 + c) == 0 && it <= a.N_save_chain0;
         const float* mu = (const float*)a.target.mu;
         if (md == MD_FIRST) {
             const int L = w.L[m];
             sL = (unsigned long long)L; sL2 = (unsigned long long)L * L;
             if (w.init[m]) {                                                        // samplers.py:416-420
                 const float E0 = V + w.K0[m];
-                a.E_chain[(size_t)m * Lrow] = (double)E0; a.dE_chain[(size_t)m * Lrow] = 0.0;
+                a.E_chain[(size_t)c * Lrow] = (double)E0; a.dE_chain[(size_t)c * Lrow] = 0.0;
                 w.E_prev[m] = E0; w.init[m] = 0;
             }
             const float Ei = V + w.K_new[m];                                        // samplers.py:434-438
             w.E_init[m] = Ei;
             if (it >= a.warm_up_num) {
                 const long idx = ((it - a.warm_up_num) / a.thin_rate) % Lrow;
-                a.E_chain[(size_t)m * Lrow + idx] = (double)Ei;
-                a.dE_chain[(size_t)m * Lrow + idx] = (double)(Ei - w.E_prev[m]);
+                a.E_chain[(size_t)c * Lrow + idx] = (double)Ei;
+                a.dE_chain[(size_t)c * Lrow + idx] = (double)(Ei - w.E_prev[m]);
             }
             if (tr) {                                                               // samplers.py:442-452
                 a.phi_len[it - 1] = L + 1;
@@ -581,15 +604,16 @@ __global__ void __launch_bounds__(256) bigd_trajectory_end(hmc_random_args a, Bi
     const float* mu = (const float*)a.target.mu;
     for (int e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
         const int ent = w.list[e];
-        const long m = ent & 0x7fffffff;
+        const long m = ent & 0x7fffffff;                                            // row
+        const long c = w.perm[m];                                                   // its chain
         const bool accepted = ent < 0;
         float* xr = w.x + (size_t)m * D;
         float* x0r = w.x0 + (size_t)m * D;
         int it = w.it[m];
         const bool keep = it >= a.warm_up_num;
-        float* dst = keep ? (float*)a.q_chain + ((size_t)m * Lrow + ((it - a.warm_up_num) / a.thin_rate) % Lrow) * D : nullptr;
+        float* dst = keep ? (float*)a.q_chain + ((size_t)c * Lrow + ((it - a.warm_up_num) / a.thin_rate) % Lrow) * D : nullptr;
         const bool last = it >= a.iter_end;
-        float* sq = last ? (float*)a.state_q + (size_t)m * D : nullptr;
+        float* sq = last ? (float*)a.state_q + (size_t)c * D : nullptr;
         if (accepted) {                                                             // samplers.py:463-469
             for (int j = 4 * lane; j < D; j += 128) {
                 const float4 v = *reinterpret_cast<const float4*>(xr + j);
@@ -612,11 +636,11 @@ __global__ void __launch_bounds__(256) bigd_trajectory_end(hmc_random_args a, Bi
             bigd_write_parts<NPART>(w, m, D, lane, x0r);
         }
         if (last) {
-            if (lane == 0) { w.mode[m] = MD_IDLE; w.it[m] = it + 1; a.state_eprev[m] = (double)w.E_prev[m]; }
+            if (lane == 0) { w.mode[m] = MD_IDLE; w.it[m] = it + 1; a.state_eprev[c] = (double)w.E_prev[m]; }
         } else {
             it += 1;
             int L = 1; float lnu = 0.f;
-            const float Kn = bigd_draw(a, m, it, lane, w.p + (size_t)m * D, &L, &lnu);      // samplers.py:431, 441, 461
+            const float Kn = bigd_draw(a, c, it, lane, w.p + (size_t)m * D, &L, &lnu);      // samplers.py:431, 441, 461
             if (lane == 0) { w.K_new[m] = Kn; w.L[m] = L; w.lnu[m] = lnu; w.l[m] = 0; w.it[m] = it; w.mode[m] = MD_FIRST; }
         }
     }
@@ -696,6 +720,8 @@ size_t carve(BigdWs& w, unsigned char* ws, long Nchain, int D, int npart, int bn
     w.tile_active = (int*)take((Ncp / BM) * 4);
     w.list = (int*)take(Ncp * 4);
     w.counters = (int*)take(64);
+    w.perm = (int*)take(Ncp * 4);
+    w.plan = (int*)take(Ncp * 4);
     return off;
 }
 
@@ -745,6 +771,17 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     if (int rc = make_map(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.p, (uint64_t)w.Ncp, D, CW, 32)) return rc;
     if (int rc = make_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.x, (uint64_t)w.Ncp, D, CW, 32)) return rc;
     w.wr = 0;                                                    // pass 0 reads buffer 0
+    {   // rows = chains sorted by planned passes, longest first (stable: equal plans keep the chain order); padding rows last
+        bigd_plan<<<(a.Nchain + 255) / 256, 256, 0, stream>>>(a, w.plan);
+        std::vector<int> plan_h(a.Nchain), perm_h(w.Ncp, -1);
+        HMC_CUDA_CHECK(cudaMemcpyAsync(plan_h.data(), w.plan, sizeof(int) * a.Nchain, cudaMemcpyDeviceToHost, stream));
+        HMC_CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < a.Nchain; ++i) perm_h[i] = i;
+        if (getenv("HMC_B200_BIGD_NOSORT") == nullptr)
+            std::stable_sort(perm_h.begin(), perm_h.begin() + a.Nchain, [&](int x, int y) { return plan_h[x] > plan_h[y]; });
+        HMC_CUDA_CHECK(cudaMemcpyAsync(w.perm, perm_h.data(), sizeof(int) * w.Ncp, cudaMemcpyHostToDevice, stream));
+        HMC_CUDA_CHECK(cudaStreamSynchronize(stream));                      // (perm_h leaves scope)
+    }
     bigd_init<NPART><<<(w.Ncp + 3) / 4, 128, 0, stream>>>(a, w);
     const int ntile_rows = w.Ncp / BM;
     HMC_CUDA_CHECK(cudaMemsetAsync(w.tile_active, 0xff, (size_t)ntile_rows * 4, stream));
