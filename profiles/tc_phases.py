@@ -32,4 +32,12 @@ for name, o, n in (("bookkeeping warps (slice 0)", 0, 4), ("other worker warps",
     print("  %s: passes/warp %.0f; cycles per pass: apply commands %.0f | wait for MMA %.0f | TMEM read + update + re-split + TMEM write %.0f | "
           "S1 arrive + group barrier A %.0f | %s %.0f | group barrier B %.0f" % (name, steps / (148 * n), v[o + 7] / steps, v[o + 0] / steps, v[o + 1] / steps, v[o + 2] / steps,
                                                          "bookkeeping (P2)" if o == 0 else "momentum draws", v[o + 3] / steps, v[o + 6] / steps))
+try:
+    lib.hmc_debug_tc_apply.argtypes = [C.POINTER(C.c_ulonglong)]
+    ap = (C.c_ulonglong * 8)(); lib.hmc_debug_tc_apply(ap)
+    nw = v[5] + v[13]
+    print("  inside apply (all worker warps, cycles per pass): command words + new / parked chains %.0f | start-point rows (accepted) %.0f | restore / take loads %.0f | warp sync %.0f"
+          % (ap[0] / nw, ap[1] / nw, ap[2] / nw, ap[3] / nw))
+except Exception as exc:
+    print("  (no apply breakdown: %r)" % exc)
 print("  issuing warp: %.0f cycles per pass inside the MMA issue" % (v[4] / (v[5] / 4)))

@@ -49,6 +49,7 @@ __device__ volatile int* g_tc_dbg = nullptr;
 
 #ifdef HMC_PROFILE_PHASES
 __device__ unsigned long long g_tc_cycles[16];     // [0..8) bookkeeping warps, [8..16) the others; slot 4 = issuing warp
+__device__ unsigned long long g_tc_apply[8];       // inside 'apply commands': [0] command words + new / parked chains, [1] start-point rows, [2] restore / take loads, [3] warp sync
 #define TP_T(x) const unsigned int x = (unsigned int)clock()
 #define TP_ADD(i, a, b) tph[i] += (b) - (a)
 #else
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     int it_end = 0, sub = 0;         // last iteration and sub-block index of the unit being run
     int wait_unit = -1;              // dequeued unit waiting for its predecessor (-1 none, -2 queue empty)
     const bool thin1 = a.thin_rate == 1;
+    const bool ring = a.store_ring > 0;
     int publish = 0;                 // passes until a finished unit's state (copied by a copying warp) is announced
     int pn = 0;                      // pass number
     unsigned pend = 0;               // chains of my group with a pending momentum request (snapshot at the group barrier)
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     bool have_grad = false;          // a gradient pass has been issued and its accumulator is to be consumed
 #ifdef HMC_PROFILE_PHASES
     unsigned int tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int tpa[4] = {0, 0, 0, 0};
 #endif
 
     {                                // defined operand rows before the first pass: all parts zero (K padding included)
@@ -427,11 +430,17 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                 }
             }
+#ifdef HMC_PROFILE_PHASES
+            const unsigned int ta1 = (unsigned int)clock(); tpa[0] += ta1 - t0;
+#endif
             if (cmd & CMD_STORE_Q0) {                                 // accepted: the proposal is the new start point
 #pragma unroll
                 for (int c = 0; c < 7; ++c)
                     if (c < nch4) *reinterpret_cast<float4*>(q0r + 4 * c) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
             }
+#ifdef HMC_PROFILE_PHASES
+            const unsigned int ta2 = (unsigned int)clock(); tpa[1] += ta2 - ta1;
+#endif
             {
                 const int rs = (cmd & (CMD_RESTORE | CMD_NEW | CMD_PARK)) != 0, tk = (cmd & (CMD_TAKE | CMD_PARK)) != 0;
                 const uint32_t qa = smem_u32(q0r), sa = smem_u32(str);
@@ -443,10 +452,19 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                 }
             }
+#ifdef HMC_PROFILE_PHASES
+            const unsigned int ta3 = (unsigned int)clock(); tpa[2] += ta3 - ta2;
+#endif
         }
+#ifdef HMC_PROFILE_PHASES
+        const unsigned int ta4 = (unsigned int)clock();
+#endif
         __syncwarp();
         TP_T(t0b);
         TP_ADD(7, t0, t0b);
+#ifdef HMC_PROFILE_PHASES
+        tpa[3] += t0b - ta4;
+#endif
         // ===== P1b. consume the gradient: thread-local leapfrog update of the slice (samplers.py:835-837), re-split ======
         if (have_grad) {
             {
@@ -550,7 +568,10 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     }
                     E_init = V + Knew;                                          // samplers.py:434-438
                     if (it >= a.warm_up_num) {
-                        const long idx = ((thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate)) % Lrow;
+                        // (stored index: below L_chain by construction; only a ring of the last store_ring samples wraps.  The 64-bit
+                        //  `% Lrow` here and at the trajectory end was a software division in the bookkeeping's latency chain.)
+                        int idx = thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate;
+                        if (ring) idx = (int)((unsigned int)idx % (unsigned int)Lrow);
                         a.E_chain[(size_t)m * Lrow + idx] = (double)E_init;
                         a.dE_chain[(size_t)m * Lrow + idx] = (double)(E_init - E_prev);
                     }
@@ -565,7 +586,11 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
                     const bool keep = it >= a.warm_up_num;
                     if (accepted) { sh->cnt[keep ? 1 : 0][chain] += 1ull; cmd |= CMD_STORE_Q0; }
                     else cmd |= CMD_RESTORE;
-                    if (keep) oreq = ((int)((long)(thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate) % Lrow) + 1) | OUT_SAMPLE;
+                    if (keep) {
+                        int idx = thin1 ? it - a.warm_up_num : (it - a.warm_up_num) / a.thin_rate;
+                        if (ring) idx = (int)((unsigned int)idx % (unsigned int)Lrow);
+                        oreq = (idx + 1) | OUT_SAMPLE;
+                    }
                     if (tr && it <= a.N_save_chain0) a.decision_chain[it - 1] = accepted ? 1 : 0;
                     if (it >= it_end) {                                         // unit finished: its position goes to state_q
                         a.state_eprev[m] = (double)E_prev;
@@ -689,6 +714,7 @@ __global__ void __launch_bounds__(TC_NT, 1) hmc_random_tc_kernel(const hmc_rando
     }
 #ifdef HMC_PROFILE_PHASES
     if (lane == 0) for (int i = 0; i < 8; ++i) if (i != 4) atomicAdd(&g_tc_cycles[(slice == 0 ? 0 : 8) + i], (unsigned long long)tph[i]);
+    if (lane == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_tc_apply[i], (unsigned long long)tpa[i]);
 #endif
 
     TC_MARK(30);
@@ -715,10 +741,11 @@ extern "C" int hmc_debug_tc_progress(int* mapped) { volatile int* p = mapped; re
 
 #ifdef HMC_PROFILE_PHASES
 extern "C" int hmc_debug_tc_cycles(unsigned long long* out16, int reset) {
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)); return 0; }
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_cycles, z, sizeof(z)); cudaMemcpyToSymbol(g_tc_apply, z, sizeof(unsigned long long) * 8); return 0; }
     cudaMemcpyFromSymbol(out16, g_tc_cycles, sizeof(unsigned long long) * 16);
     return 0;
 }
+extern "C" int hmc_debug_tc_apply(unsigned long long* out8) { cudaMemcpyFromSymbol(out8, g_tc_apply, sizeof(unsigned long long) * 8); return 0; }
 #endif
 
 constexpr size_t tc_smem_bytes(int npart) {
