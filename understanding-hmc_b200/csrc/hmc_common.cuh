@@ -43,6 +43,15 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return o;
 }
 
+// stored-sample index of iteration `it` (samplers.py:436, 468: (i - warm_up_num) // thin_rate); below L_chain by construction, so
+// only a ring of the last `store_ring` samples wraps.  32-bit on purpose: a 64-bit `% Lrow` is a software division in the middle
+// of the per-trajectory service code (measured in the tensor-core kernel: 400 cycles of its 1,800-cycle bookkeeping phase).
+__device__ __forceinline__ long hmc_store_index(int it, int warm_up_num, int thin_rate, long Lrow, bool ring) {
+    int idx = (thin_rate == 1) ? it - warm_up_num : (it - warm_up_num) / thin_rate;
+    if (ring) idx = (int)((unsigned int)idx % (unsigned int)Lrow);
+    return (long)idx;
+}
+
 enum { HMC_STREAM_MOMENTUM = 0, HMC_STREAM_SCALAR = 1, HMC_STREAM_NUTS = 2 };
 
 // 4 standard normals for dims 4*slot .. 4*slot+3 of (chain, iteration): float32 Box-Muller.

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                 // ---- the trajectory of iteration `it` ended: keep or restore the position, store the sample
                 //      (samplers.py:462-472)
                 const bool keep = it >= a.warm_up_num;
-                const long idx = keep ? ((it - a.warm_up_num) / a.thin_rate) % Lrow : 0;
+                const long idx = keep ? hmc_store_index(it, a.warm_up_num, a.thin_rate, Lrow, a.store_ring > 0) : 0;
                 if (owner) {
                     float* dst = q_chain + ((size_t)m * Lrow + idx) * D;
                     float* q0 = q0g + (size_t)m * D;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     // E_initial of the new iteration (samplers.py:434-438): V at the accepted point + new kinetic energy
                     b.Einit = b.V + (double)b.Knew;
                     if (itn >= a.warm_up_num) {
-                        const long idx = ((itn - a.warm_up_num) / a.thin_rate) % Lrow;
+                        const long idx = hmc_store_index(itn, a.warm_up_num, a.thin_rate, Lrow, a.store_ring > 0);
                         a.E_chain[(size_t)m * Lrow + idx] = b.Einit;
                         a.dE_chain[(size_t)m * Lrow + idx] = b.Einit - b.Eprev;
                     }
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) hmc_random_fast_kernel(const hm
                     }
                     b.Einit = V + (double)b.Knew;                      // samplers.py:434-438
                     if (b.it >= a.warm_up_num) {
-                        const long idx = ((b.it - a.warm_up_num) / a.thin_rate) % Lrow;
+                        const long idx = hmc_store_index(b.it, a.warm_up_num, a.thin_rate, Lrow, a.store_ring > 0);
                         a.E_chain[(size_t)b.m * Lrow + idx] = b.Einit;
                         a.dE_chain[(size_t)b.m * Lrow + idx] = b.Einit - b.Eprev;
                     }
