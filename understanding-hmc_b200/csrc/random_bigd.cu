@@ -44,8 +44,12 @@ constexpr int BN_MAX = 256;        // dimensions per tile (UMMA N; fp32 accumula
 constexpr int kStageK = 128;       // stages x BK
 constexpr int kMaxCluster = 4;     // largest cluster of row blocks (the chain count is padded to whole clusters)
 constexpr int CW = 16;             // epilogue chunk: 16 columns of a warp's 32 chains
-constexpr int NEPI = 4;            // epilogue warps: one per TMEM lane quarter
-constexpr int NBUF = 3;            // chunk buffers per epilogue warp (one in arithmetic, one being stored, one loading)
+#ifndef BIGD_NEPI
+#define BIGD_NEPI 4
+#endif
+constexpr int NEPI = BIGD_NEPI;    // epilogue warps: one (4) or two (8, alternating chunks) per TMEM lane quarter
+constexpr int NBUF = NEPI == 4 ? 3 : 2;   // chunk buffers per epilogue warp (one in arithmetic, one being stored, one loading)
+constexpr int NHALF = NEPI / 4;
 constexpr int NTHREADS = 64 + 32 * NEPI;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int EPB_PX = 32 * CW * 4;           // one float32 array of a chunk: 32 rows x 64 bytes, SWIZZLE_64B
 constexpr int EPB_PART = 32 * CW * 2;         // one 16-bit part of a chunk: 32 rows x 32 bytes, SWIZZLE_32B
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
         //       position; NBUF chunk buffers per warp, the load of chunk g + 2 is issued when the store of chunk g - 1 has left its
         //       buffer.  (The first version moved every element through registers -> padded tile -> registers twice: ~150 LSU
         //       instructions per 256 elements, and ran at 26 % tensor-pipe activity whatever the operand pipeline did.) ==========
-        const int quarter = warp & 3, ew = warp - 2;
+        const int quarter = warp & 3, ew = warp - 2, half = ew >> 2;    // (two warps of a quarter take alternating chunks)
         unsigned char* ebase = epi + ew * EPI_WARP_BYTES;
         uint64_t* ef = efull + ew * NBUF;
         constexpr int NCH = BN / CW;                        // chunks of a tile
@@ -322,13 +326,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
         // prefetch cursor: (pf_t, pf_c) = the next chunk to request, pf_g its number in the stream
         int pf_t = cid - ncl;
         pf_t = next_live(pf_t);
-        int pf_c = 0;
+        int pf_c = half;
         uint32_t pf_g = 0, g = 0;
         auto prefetch_one = [&]() {
             if (pf_t >= ntiles) return;
             issue_chunk(pf_t, pf_c, pf_g);
             ++pf_g;
-            if (++pf_c == NCH) { pf_c = 0; pf_t = next_live(pf_t); }
+            if ((pf_c += NHALF) >= NCH) { pf_c = half; pf_t = next_live(pf_t); }
         };
         prefetch_one();
         prefetch_one();
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;");
             float hv = 0.f, hk = 0.f;
             if (live) {
-                for (int c = 0; c < NCH; ++c, ++g) {
+                for (int c = half; c < NCH; c += NHALF, ++g) {
                     const int buf = g % NBUF;
                     unsigned char* bp = ebase + buf * EPI_BUF_BYTES;
                     const int c0 = nt * BN + c * CW;
@@ -404,15 +408,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) bigd_gemm_step(const __grid_const
                         const int r = (int)row0 + (lane < 2 ? 0 : (lane - 2) * (int)part_rows_a);
                         tma_store_2d(mp, src, c0, r);
                         bulk_commit();                                   // (bulk groups are per thread: each storing lane tracks its own)
-                        bulk_wait_read<1>();                             // the stores of chunk g - 1 have left their buffer: chunk g + 2 goes there
+                        bulk_wait_read<NBUF - 2>();                      // the stores of chunk g + 2 - NBUF have left their buffer: chunk g + 2 goes there
                     }
                     __syncwarp();
                     prefetch_one();
                 }
             }
             if (chain < Nchain) {
-                float* rd = w.red + ((size_t)chain * NT + nt) * 4;
-                rd[0] = hv; rd[1] = hk; rd[2] = 0.f; rd[3] = 0.f;
+                float* rd = w.red + ((size_t)chain * NT + nt) * 4 + half * 2;
+                rd[0] = hv; rd[1] = hk;
+                if (NHALF == 1) { rd[2] = 0.f; rd[3] = 0.f; }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
@@ -729,7 +734,7 @@ template <int NPART, int BN, int BK, int STAGES>
 constexpr size_t gemm_smem_bytes() {
     return (size_t)STAGES * NPART * (BM * BK * 2 + BN * BK * 2) + (size_t)NEPI * NBUF * (2 * EPB_PX + NPART * EPB_PART) + (2 * STAGES + 4 + NEPI * NBUF) * 8 + 64;
 }
-static_assert(gemm_smem_bytes<2, 256, 32, 3>() <= 232448 && gemm_smem_bytes<3, 128, 32, 2>() <= 232448,
+static_assert(gemm_smem_bytes<2, 256, 32, (NEPI == 4 ? 3 : 2)>() <= 232448 && gemm_smem_bytes<3, 128, 32, 2>() <= 232448,
               "shared memory of the large-D GEMM exceeds 227 KB");
 
 template <int NPART, int BN, int CL, int BK, int STAGES>
@@ -878,6 +883,7 @@ int hmc_random_run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     // full pass at fp16x2 and 19 % of a bf16x3 run.
     int cl = 2;
     if (const char* e = getenv("HMC_B200_BIGD_CLUSTER")) cl = atoi(e);
-    if (fp16) return cl == 2 ? run_bigd<2, 256, 2, 32, 3>(a, stream) : run_bigd<2, 256, 1, 32, 3>(a, stream);
+    constexpr int ST2 = NEPI == 4 ? 3 : 2;           // operand stages that fit beside the epilogue buffers
+    if (fp16) return cl == 2 ? run_bigd<2, 256, 2, 32, ST2>(a, stream) : run_bigd<2, 256, 1, 32, ST2>(a, stream);
     return cl == 2 ? run_bigd<3, 128, 2, 32, 2>(a, stream) : run_bigd<3, 128, 1, 32, 2>(a, stream);
 }

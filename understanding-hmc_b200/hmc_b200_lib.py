@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhmc_b200.so")
+LIB_PATH = os.environ.get("HMC_B200_LIB") or os.path.join(_HERE, "libhmc_b200.so")      # (HMC_B200_LIB: a profiling / variant build)
 
 HMC_F32, HMC_F64 = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_TC, KERNEL_BIGD = 0, 1, 2, 3, 4
