@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <vector>
 #include <algorithm>
+#include <exception>
 
 namespace {
 
@@ -776,7 +777,7 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
     if (int rc = make_map(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.p, (uint64_t)w.Ncp, D, CW, 32)) return rc;
     if (int rc = make_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.x, (uint64_t)w.Ncp, D, CW, 32)) return rc;
     w.wr = 0;                                                    // pass 0 reads buffer 0
-    {   // rows = chains sorted by planned passes, longest first (stable: equal plans keep the chain order); padding rows last
+    try {   // rows = chains sorted by planned passes, longest first (stable: equal plans keep the chain order); padding rows last
         bigd_plan<<<(a.Nchain + 255) / 256, 256, 0, stream>>>(a, w.plan);
         std::vector<int> plan_h(a.Nchain), perm_h(w.Ncp, -1);
         HMC_CUDA_CHECK(cudaMemcpyAsync(plan_h.data(), w.plan, sizeof(int) * a.Nchain, cudaMemcpyDeviceToHost, stream));
@@ -786,6 +787,9 @@ int run_bigd(const hmc_random_args& a, cudaStream_t stream) {
             std::stable_sort(perm_h.begin(), perm_h.begin() + a.Nchain, [&](int x, int y) { return plan_h[x] > plan_h[y]; });
         HMC_CUDA_CHECK(cudaMemcpyAsync(w.perm, perm_h.data(), sizeof(int) * w.Ncp, cudaMemcpyHostToDevice, stream));
         HMC_CUDA_CHECK(cudaStreamSynchronize(stream));                      // (perm_h leaves scope)
+    } catch (const std::exception& e) {                    // (no exception crosses the C boundary)
+        hmc_set_error("large-D kernel: host-side row plan failed: %s", e.what());
+        return HMC_E_CUDA;
     }
     bigd_init<NPART><<<(w.Ncp + 3) / 4, 128, 0, stream>>>(a, w);
     const int ntile_rows = w.Ncp / BM;
