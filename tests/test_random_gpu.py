@@ -242,6 +242,39 @@ def test_leap_frog_primitive_matches_oracle(dtype, tol):
         np.testing.assert_allclose(p3, pr, rtol=0, atol=10 * tol); np.testing.assert_allclose(q3, qr, rtol=0, atol=10 * tol)
 
 
+@pytest.mark.parametrize("kernel,D", [("tc", 100), ("fast", 100), ("generic", 12), ("bigd", 256)])
+def test_store_ring_keeps_the_last_stored_samples(kernel, D):
+    """hmc_random_args.store_ring = R (C-ABI only: streaming runs keep the last R stored samples per chain): stored index j lives in
+    row j % R of q_chain / E_chain / dE_chain.  Same seed => the ring run's rows equal the full run's last R samples bit for bit."""
+    import torch
+    import hmc_b200_lib as L
+    import samplers as S
+    Nchain, Niter, warm, thin, R = 300, 31, 4, 2, 5
+    spec = S.MVNSpec.from_cov(np.zeros(D), O.equicorrelated_cov(D, 0.6))
+    q_start = (np.random.RandomState(D).standard_normal((Nchain, D)) * 1.2).astype(np.float32)
+    kw = dict(Nchain=Nchain, Niter=Niter, thin_rate=thin, warm_up_num=warm, sampler_type="Random", dt=0.1, L_low=3, L_high=9,
+              dtype="float32", seed=41, target=spec, kernel=kernel)
+    F = S.HMC_sampler(D, None, None, **kw)
+    F.gen_sample(q_start, verbose=False, quiet=True)
+    Lc = F.L_chain
+    assert Lc == 1 + (Niter - warm) // thin and Lc > R + 2
+    H = S.HMC_sampler(D, None, None, **kw)
+    run = H.prepare_random(q_start)
+    a = run["args"]
+    qr = torch.zeros((Nchain, R, D), dtype=torch.float32, device="cuda")
+    Er = torch.zeros((Nchain, R), dtype=torch.float64, device="cuda")
+    dEr = torch.zeros((Nchain, R), dtype=torch.float64, device="cuda")
+    a.q_chain, a.E_chain, a.dE_chain, a.store_ring = qr.data_ptr(), Er.data_ptr(), dEr.data_ptr(), R
+    a.iter_begin, a.iter_end = 0, Niter
+    L.check(L.load().hmc_random_run(a, L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    qr, Er, dEr = qr.cpu().numpy(), Er.cpu().numpy(), dEr.cpu().numpy()
+    for j in range(Lc - R, Lc):
+        np.testing.assert_array_equal(qr[:, j % R], F.q_chain[:, j].astype(np.float32))
+        np.testing.assert_array_equal(Er[:, j % R], F.E_chain[:, j, 0])
+        np.testing.assert_array_equal(dEr[:, j % R], F.dE_chain[:, j, 0])
+
+
 def test_target_extraction_and_errors():
     import samplers as S
     import hmc_b200_lib as L
