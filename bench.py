@@ -566,6 +566,7 @@ def main():
                            dt=DT, L_low=L_LOW, L_high=L_HIGH, dtype="float32", kernel="auto", seed=77 + i,
                            chain_id0=id0, target=spec, distributed=(world > 1))
         barrier()
+        U.D2H_BYTES[0] = 0
         t0 = time.perf_counter()
         H2.gen_sample(q_pinned, verbose=False, quiet=True)       # H2D of q_start inside
         H2.compute_convergence_stats()                           # GPU reductions (+ NCCL), D2H of the partial sums
@@ -577,6 +578,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ll)
         if i >= 1:
+            e2e_d2h = int(U.D2H_BYTES[0])                        # counted where the mirror reads results back (utils._host)
             e2e_ms.append(float(tt.item()) * 1e3)
             e2e_L.append(float(ll.item()))
             ess = {"what": "reference-formula n_eff (utils.py:77-159) of the stored samples of one step's run, over its wall time incl. diagnostics",
@@ -589,7 +591,7 @@ def main():
     log("e2e done")
     e2e_value = float(np.sum(e2e_L) / (np.sum(e2e_ms) * 1e-3))
     h2d = Nc * D * 4
-    d2h = (U.ROW_LAGS + 32) * D * 8 + 16 * 8          # packed statistics buffer + counters; further lag chunks add 32*D*8 each
+    d2h = e2e_d2h                                     # packed statistics buffer, counters, the all-lags variogram buffer
 
     secondary = None
     if not args.no_secondary:

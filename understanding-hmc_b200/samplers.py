@@ -451,9 +451,9 @@ class HMC_sampler(sampler):
         # one packed buffer: local counters and chain count, all-reduced copy behind them -> one collective, one D2H
         counters[4] = Nc
         if self.distributed:
-            both = torch.cat([counters, self._all_reduce(torch, counters.clone())]).cpu().numpy()
+            both = _utils._host(torch.cat([counters, self._all_reduce(torch, counters.clone())]))
         else:
-            both = torch.cat([counters, counters]).cpu().numpy()
+            both = _utils._host(torch.cat([counters, counters]))
         self.sum_L_local = int(both[2])
         acc_warm, acc_post, sumL, sumL2, nchain_all = (int(v) for v in both[8:13])
         self.sum_L = sumL

@@ -139,9 +139,9 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
         world = dist.get_world_size(group=grp)
         allbuf = _scratch("stats_all", (world, ROW_LAGS + lag_chunk, D), torch.float64, device)
         dist.all_gather_into_tensor(allbuf.view(world * (ROW_LAGS + lag_chunk), D), buf, group=grp)
-        host = allbuf.cpu().numpy()
+        host = _host(allbuf)
     else:
-        host = buf.cpu().numpy()[None]
+        host = _host(buf)[None]
     m_r = np.rint(host[:, ROW_COUNT, 0])                            # split chains per rank
     m = int(m_r.sum())
     W = host[:, 0].sum(axis=0) / m                                  # utils.py:112 (mean of std, Q1)
@@ -166,7 +166,7 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
             all_lags_fn(abuf)
             if distributed:
                 dist.all_reduce(abuf, group=grp)
-            rows = abuf[lag0 - 1:].cpu().numpy()
+            rows = _host(abuf[lag0 - 1:])
             nl = max_lag - lag0 + 1
         else:
             if vbuf is None:
@@ -174,7 +174,7 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
             variogram_fn(lag0, nl, vbuf)
             if distributed:
                 dist.all_reduce(vbuf, group=grp)
-            rows = vbuf[:nl].cpu().numpy()
+            rows = _host(vbuf[:nl])
         V_rows = [rows[k] / float(m * (n - (lag0 + k))) for k in range(nl)]      # utils.py:177
         if _finish_n_eff(var, V_rows, m, n, state):
             break
@@ -185,6 +185,13 @@ def _stats_from_partials(moments_fn, variogram_fn, n, D, m_local, group=None, la
 
 
 _SCRATCH = {}
+D2H_BYTES = [0]          # bytes read back from the device by the diagnostics / counters (bench.py reports them per step)
+
+
+def _host(t):
+    """Device tensor -> numpy (one D2H copy, counted)."""
+    D2H_BYTES[0] += t.numel() * t.element_size()
+    return t.cpu().numpy()
 
 
 def _scratch(name, shape, dtype, device=None):
