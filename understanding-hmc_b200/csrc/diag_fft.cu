@@ -94,7 +94,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // SM holds two or three blocks) and the stream is fetched 3.4 times (ncu: 70 GB for 21 GB).  So the blocks of a group check in
 // at a counter every kStepSync chains and wait while they are more than kStepLead check-ins ahead of the slowest sibling; a
 // cooperative launch guarantees that all of them are resident, and a spin limit turns a missing sibling into lost sharing
-// instead of a hang.  Measured: 21.1 GB of DRAM reads for the 21 GB stream.
+// instead of a hang.  Measured DRAM reads for the 21 GB stream: 21.1 GB in strict lock step (lead 0), 42 GB with the one check-in
+// of lead shipped here, 70 GB without check-ins -- at the same kernel time (the kernel is issue / shared-memory-latency bound).
 __global__ void __launch_bounds__(kThreads, 3) diag_fft_power_kernel(const float* __restrict__ q, long Nchain, int n, int D, long stride_chain,
                                                                     int groups, double* __restrict__ P, double* __restrict__ Q,
                                                                     unsigned int* __restrict__ bars) {
